@@ -1,0 +1,211 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY -- not product code, never imported by gcl_b200.
+
+CPU restatement of the reference's encode-process-decode glue so that the whole forecast step can
+be checked (and timed as the CPU baseline) on the GPU box, where /root/reference does not exist:
+
+  MLP                /root/reference/src/models.py:54-109
+  SparseGATConv      /root/reference/src/models.py:112-151
+  GraphLayer         /root/reference/src/models.py:289-440   (SimpleConv / ConvGCN / GATConv / SparseGATConv)
+  Model              /root/reference/src/models.py:443-473
+  WeatherPrediction  /root/reference/src/models.py:476-601, 776-874  (no product graph, no InteractionNet)
+  weighted MSE + AR rollout of one training step   /root/reference/src/train.py:85-102, 160-233
+
+The conv / norm arithmetic comes from oracle/pyg_shim (restated torch_geometric 2.5.3).  Module and
+parameter names equal the reference's, so state_dicts are interchangeable.  Pinned in the build
+container by tests/test_oracle.py::test_model_glue_matches_unmodified_reference (bit-exact against
+/root/reference/src/models.py run on the same shims) and on the GPU box through tests/golden/*.npz
+written by oracle/make_golden.py.  The conv arithmetic itself stays PARITY UNPINNED (see pyg_shim).
+
+Extension: inputs may be [B, G, T*F]; samples are processed one at a time exactly as batch 1.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+_here = os.path.dirname(os.path.abspath(__file__))
+for _p in ("pyg_shim", "trimesh_shim"):
+    if os.path.join(_here, _p) not in sys.path:
+        sys.path.insert(0, os.path.join(_here, _p))
+from torch_geometric.nn import GATConv, GCNConv, LayerNorm, SimpleConv  # noqa: E402
+
+from . import graphs as og  # noqa: E402
+
+
+def _truthy(v):
+    return v is True or (isinstance(v, str) and v.lower() == "true")
+
+
+class MLP(nn.Module):
+    def __init__(self, cfg: dict, input_dim: int):
+        super().__init__()
+        self.MLP = nn.ModuleList()
+        last = input_dim
+        for h in (cfg.get("mlp_hidden_dims") or []):
+            self.MLP.extend([nn.Linear(last, h), nn.PReLU()])
+            last = h
+        self.MLP.append(nn.Linear(last, cfg["output_dim"]))
+        if _truthy(cfg.get("use_layer_norm")):
+            self.MLP.append(LayerNorm(cfg["output_dim"], mode=cfg.get("layer_norm_mode")))
+
+    def forward(self, X):
+        for layer in self.MLP:
+            X = layer(X)
+        return X
+
+
+class SparseGATConv(GATConv):
+    def __init__(self, in_channels, out_channels, heads=1, concat=False, dropout=0.0, bias=True, **kw):
+        super().__init__(in_channels, out_channels, heads, concat=concat, dropout=dropout, bias=bias, **kw)
+
+    def forward(self, x, edge_index, attention_threshold=0.0, **kwargs):
+        batch_num = kwargs.get("batch_num", 1)
+        out, (edge_index, att) = super().forward(x, edge_index, return_attention_weights=True)
+        att = att.squeeze()
+        if batch_num == 0:
+            mask = (att >= attention_threshold).type(torch.bool)
+            edge_index, att = edge_index[:, mask], att[mask]
+        return out, (edge_index, att)
+
+
+class GraphLayer(nn.Module):
+    def __init__(self, cfg: dict, input_dim: int):
+        super().__init__()
+        self.layer_type = cfg["layer_type"]
+        if self.layer_type == "simple_conv":
+            self.output_dim = input_dim
+            self.layers = SimpleConv(aggr="mean")
+            return
+        assert self.layer_type in ("conv_gcn", "conv_gat", "sparse_gat"), self.layer_type
+        act = cfg.get("activation") or "prelu"
+        self.activation = {"prelu": nn.PReLU, "relu": nn.ReLU, "silu": nn.SiLU, "swish": nn.SiLU}[act]()
+        self.output_dim = cfg["output_dim"]
+        self.layers = nn.ModuleList()
+        hid = cfg.get("hidden_dims") or []
+        if self.layer_type == "sparse_gat":
+            self.layers.append(SparseGATConv(input_dim, self.output_dim,
+                                             heads=cfg["gat_props"]["num_heads"], concat=False))
+        else:
+            def conv(i, o):
+                if self.layer_type == "conv_gcn":
+                    return GCNConv(i, o)
+                return GATConv(i, o, heads=cfg["gat_props"]["num_heads"], concat=False)
+            dims = [input_dim] + list(hid)
+            for i in range(len(hid)):
+                self.layers.append(conv(dims[i], dims[i + 1]))
+                self.layers.append(self.activation)
+            self.layers.append(conv(dims[-1], self.output_dim))
+        if _truthy(cfg.get("use_layer_norm")):
+            self.layers.append(LayerNorm(self.output_dim, mode=cfg.get("layer_norm_mode")))
+
+    def forward(self, X, edge_index, attention_threshold=0.0, **kwargs):
+        if self.layer_type == "simple_conv":
+            return self.layers(x=X, edge_index=edge_index)
+        if self.layer_type == "sparse_gat":
+            for layer in self.layers:
+                if type(layer) is SparseGATConv:
+                    X, (edge_index, _) = layer.forward(X, edge_index, attention_threshold, **kwargs)
+                else:
+                    X = layer(X)
+            return X, edge_index
+        for layer in self.layers:
+            X = layer(X, edge_index) if type(layer) in (GCNConv, GATConv) else layer(X)
+        return X
+
+
+class Model(nn.Module):
+    def __init__(self, cfg: dict, input_dim: int):
+        super().__init__()
+        self.mlp = MLP(cfg["mlp"], input_dim) if cfg.get("mlp") else None
+        gin = cfg["mlp"]["output_dim"] if cfg.get("mlp") else input_dim
+        self.graph_layer = GraphLayer(cfg["gcn"], gin)
+        self.output_dim = self.graph_layer.output_dim
+
+    def forward(self, X, edge_index, attention_threshold=0.0, **kwargs):
+        if self.mlp is not None:
+            X = self.mlp(X)
+        return self.graph_layer(X=X, edge_index=edge_index, attention_threshold=attention_threshold, **kwargs)
+
+
+class WeatherPrediction(nn.Module):
+    """cfg = {"graph": ..., "pipeline": ..., "data": ...} with the reference's config.json schema."""
+
+    def __init__(self, cfg: dict, nlat: int, nlon: int, graphs: dict = None):
+        super().__init__()
+        g = graphs or og.build_graphs(nlat, nlon, cfg["graph"]["mesh_levels"],
+                                      cfg["graph"]["grid2mesh_radius_query"])
+        self.G, self.M = g["num_grid"], g["num_mesh"]
+        self.obs_window = cfg["data"]["obs_window_used"]
+        self.num_features = cfg["data"]["num_features_used"]
+        self.total_feature_size = self.obs_window * self.num_features
+        self.encoding_graph = torch.as_tensor(g["g2m"])
+        self.processing_graph = torch.as_tensor(g["mesh"])
+        self.decoding_graph = torch.as_tensor(g["m2g"])
+        self.init_grid_features = torch.as_tensor(g["grid_feats"])
+        self.init_mesh_features = torch.as_tensor(g["mesh_feats"])
+        pipe = cfg["pipeline"]
+        self.using_sparse_gat = pipe["processor"]["gcn"]["layer_type"] == "sparse_gat"
+        self.encoder = Model(pipe["encoder"], self.total_feature_size + 6)
+        self.processor = Model(pipe["processor"], self.encoder.output_dim)
+        self.decoder = Model(pipe["decoder"], self.processor.output_dim)
+
+    def _one(self, X, attention_threshold, **kwargs):
+        X = torch.cat((X, self.init_grid_features), dim=-1)
+        mesh = torch.cat((torch.zeros(self.M, self.total_feature_size), self.init_mesh_features), dim=-1)
+        enc = self.encoder(X=torch.cat((X, mesh), dim=0), edge_index=self.encoding_graph)
+        grid_lat, mesh_lat = enc[: self.G], enc[self.G:]
+        if self.using_sparse_gat:
+            proc, new_ei = self.processor(X=mesh_lat, edge_index=self.processing_graph,
+                                          attention_threshold=attention_threshold, **kwargs)
+            self.processing_graph = new_ei
+        else:
+            proc = self.processor(X=mesh_lat, edge_index=self.processing_graph,
+                                  attention_threshold=attention_threshold)
+        dec = self.decoder(X=torch.cat((grid_lat, proc), dim=0), edge_index=self.decoding_graph)
+        return dec[: self.G]
+
+    def forward(self, X, attention_threshold=0.0, **kwargs):
+        if X.dim() == 3 and X.size(0) > 1:
+            return torch.stack([self._one(x, attention_threshold, **kwargs) for x in X])
+        return self._one(X.squeeze(0) if X.dim() == 3 else X, attention_threshold, **kwargs)
+
+
+def lat_weights(nlat: int, nlon: int) -> torch.Tensor:
+    """train.py:53-72 (regular grid): cos(lat)/mean, expanded [lon, lat] then flattened -> [1,G,1]."""
+    w = torch.cos(torch.deg2rad(torch.linspace(-90, 90, nlat)))
+    w = w / w.mean()
+    return w.view(1, -1).expand(nlon, nlat).reshape(-1).view(1, -1, 1)
+
+
+def weighted_mse(pred, target, lat_w=None):
+    """train.py:85-102 without channel / spatial masks (BASELINE configs set none)."""
+    diff = (pred - target) ** 2
+    w = torch.ones_like(diff)
+    if lat_w is not None:
+        w = w * lat_w
+    return (diff * w).sum() / w.sum().clamp_min(1e-12)
+
+
+def training_loss(model: WeatherPrediction, X, y, ar_steps: int, lat_w=None, threshold=0.0,
+                  use_residual=True, **kwargs):
+    """Loss of one train_epoch iteration (train.py:173-231): AR rollout, BPTT through it."""
+    if X.dim() == 2:
+        X, y = X.unsqueeze(0), y.unsqueeze(0)
+    Bn, G, _ = X.shape
+    obs = model.obs_window
+    C = X.shape[-1] // obs
+    tsteps = y.shape[-1] // C
+    ys = y.view(Bn, G, tsteps, C)
+    state = X.view(Bn, G, obs, C)
+    steps = min(ar_steps, tsteps)
+    loss = 0
+    for s in range(steps):
+        delta = model(X=state.reshape(Bn, G, -1), attention_threshold=threshold, **kwargs)
+        if delta.dim() == 2:
+            delta = delta.unsqueeze(0)
+        out = state[:, :, -1, :] + delta if use_residual else delta
+        loss = loss + weighted_mse(out, ys[:, :, s, :], lat_w)
+        state = torch.cat([state[:, :, 1:, :], out.unsqueeze(2)], dim=2)
+    return loss / steps
