@@ -1,0 +1,25 @@
+// Error state + version for the gcl_b200 C ABI.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace gcl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail_cuda(cudaError_t e, const char* what) {
+  set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+  return GCL_ERR_CUDA;
+}
+
+}  // namespace gcl
+
+extern "C" int gcl_version(void) { return 1; }
+extern "C" const char* gcl_last_error(void) { return gcl::g_err; }

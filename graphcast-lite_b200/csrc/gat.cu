@@ -1,0 +1,491 @@
+// K4/K5: GATConv / SparseGATConv message passing, forward and backward, fp32, no atomics.
+//
+// Replaces PyG GATConv.edge_update + softmax + propagate (+ head mean / bias), which the reference
+// uses at /root/reference/src/models.py:336-357 (GATConv) and :112-151 (SparseGATConv):
+//   e_ij   = LeakyReLU(a_src[j] + a_dst[i])                      (j -> i, self loops included)
+//   alpha  = exp(e - max_i) / (sum_i exp(.) + 1e-16)             (torch_geometric.utils.softmax)
+//   out_i  = mean_h / concat_h ( sum_j alpha_ijh z_jh ) + bias
+// One warp owns one (sample, receiver).  The 32 lanes first run over the receiver's incoming edges
+// (max, sum, alpha: segment softmax with warp shuffles), then switch to "S slots x L lanes": each slot
+// gathers a different neighbour row, L lanes each hold one 128-bit word of the C-wide head slice, and
+// the slots are folded with a fixed-order shuffle tree.  alpha is written once in CSR order (kept for
+// backward) and optionally scattered to PyG edge order (return_attention_weights / pruning).
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace gcl {
+namespace {
+
+constexpr int kWarps = 8;
+
+__device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : slope * v; }
+
+template <int VW>
+struct W;
+template <>
+struct W<4> {
+  using T = float4;
+  static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ T load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ void store(float* p, T v) { *reinterpret_cast<float4*>(p) = v; }
+  static __device__ __forceinline__ void fma(T& a, float w, T v) {
+    a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+  }
+  static __device__ __forceinline__ T add(T a, T b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+  static __device__ __forceinline__ T scale(T a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+  static __device__ __forceinline__ float dot(T a, T b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+  static __device__ __forceinline__ T xor_add(T a, int o) {
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, o); a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+    a.z += __shfl_xor_sync(0xffffffffu, a.z, o); a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+    return a;
+  }
+};
+template <>
+struct W<1> {
+  using T = float;
+  static __device__ __forceinline__ T zero() { return 0.f; }
+  static __device__ __forceinline__ T load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, T v) { *p = v; }
+  static __device__ __forceinline__ void fma(T& a, float w, T v) { a = fmaf(w, v, a); }
+  static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+  static __device__ __forceinline__ T scale(T a, float s) { return a * s; }
+  static __device__ __forceinline__ float dot(T a, T b) { return a * b; }
+  static __device__ __forceinline__ T xor_add(T a, int o) { return a + __shfl_xor_sync(0xffffffffu, a, o); }
+};
+
+// a_src[row,h] = <z[row,h,:], att_src[h,:]>, same for dst.  One warp per row.
+__global__ void gat_scores_kernel(const float* __restrict__ z, const float* __restrict__ att_src,
+                                  const float* __restrict__ att_dst, float* __restrict__ a_src,
+                                  float* __restrict__ a_dst, int64_t rows, int H, int C) {
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* zr = z + row * H * C;
+  for (int h = 0; h < H; ++h) {
+    float s = 0.f, d = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = zr[h * C + c];
+      s = fmaf(v, __ldg(att_src + h * C + c), s);
+      d = fmaf(v, __ldg(att_dst + h * C + c), d);
+    }
+    s = warp_sum(s);
+    d = warp_sum(d);
+    if (lane == 0) {
+      a_src[row * H + h] = s;
+      a_dst[row * H + h] = d;
+    }
+  }
+}
+
+template <int VW, int L>
+__global__ void __launch_bounds__(kWarps * 32)
+    gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                   const int32_t* __restrict__ perm, const float* __restrict__ z, const float* __restrict__ a_src,
+                   const float* __restrict__ a_dst, const float* __restrict__ bias, float* __restrict__ out,
+                   float* __restrict__ alpha_csr, float* __restrict__ alpha_pyg, int64_t N, int64_t nnz, int H,
+                   int C, int concat, float slope) {
+  using V = W<VW>;
+  constexpr int S = 32 / L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane & (L - 1), slot = lane / L;
+  const int64_t i = (int64_t)blockIdx.x * kWarps + warp;
+  const int64_t b = blockIdx.y;
+  if (i >= N) return;
+  const int32_t beg = rowptr[i], end = rowptr[i + 1];
+  const int HC = H * C, Cout = concat ? HC : C;
+  const int64_t nb = b * N;
+  const float* zb = z + nb * HC;
+  const int words = (C + VW - 1) / VW;  // words per head slice
+  const int nchunks = (words + L - 1) / L;
+  const float inv_h = 1.f / (float)H;
+
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    const int off = (chunk * L + gl) * VW;
+    const bool live = off < C;
+    typename V::T total = V::zero();
+    for (int h = 0; h < H; ++h) {
+      const float adi = a_dst[(nb + i) * H + h];
+      float m = -INFINITY;
+      for (int32_t k = beg + lane; k < end; k += 32)
+        m = fmaxf(m, leaky(a_src[(nb + col[k]) * H + h] + adi, slope));
+      m = warp_max(m);
+      float ssum = 0.f;
+      for (int32_t k = beg + lane; k < end; k += 32)
+        ssum += expf(leaky(a_src[(nb + col[k]) * H + h] + adi, slope) - m);
+      ssum = warp_sum(ssum) + 1e-16f;
+
+      typename V::T acc = V::zero();
+      for (int32_t base = beg; base < end; base += 32) {
+        const int32_t k = base + lane;
+        const int n = min(32, end - base);
+        int32_t c_reg = 0;
+        float a_reg = 0.f;
+        if (k < end) {
+          c_reg = col[k];
+          a_reg = expf(leaky(a_src[(nb + c_reg) * H + h] + adi, slope) - m) / ssum;
+          if (chunk == 0) {
+            alpha_csr[(b * nnz + k) * H + h] = a_reg;
+            if (alpha_pyg) alpha_pyg[(b * nnz + perm[k]) * H + h] = a_reg;
+          }
+        }
+        for (int jj = 0; jj < n; jj += S) {
+          const int j = jj + slot;
+          const int src = j < n ? j : 0;
+          const int32_t c = __shfl_sync(0xffffffffu, c_reg, src);
+          const float a = __shfl_sync(0xffffffffu, a_reg, src);
+          if (j < n && live) V::fma(acc, a, V::load(zb + (int64_t)c * HC + h * C + off));
+        }
+      }
+#pragma unroll
+      for (int o = L; o < 32; o <<= 1) acc = V::xor_add(acc, o);
+      if (concat) {
+        if (live && slot == 0) {
+          if (bias) acc = V::add(acc, V::load(bias + h * C + off));
+          V::store(out + (nb + i) * Cout + h * C + off, acc);
+        }
+      } else {
+        total = V::add(total, acc);
+      }
+    }
+    if (!concat && live && slot == 0) {
+      total = V::scale(total, inv_h);
+      if (bias) total = V::add(total, V::load(bias + off));
+      V::store(out + (nb + i) * Cout + off, total);
+    }
+  }
+}
+
+// Backward pass 1, one warp per (sample, receiver i):
+//   dalpha_k = <do_h(i), z[col_k, h]>;  t = sum_k alpha_k dalpha_k;  g_k = alpha_k (dalpha_k - t) * LeakyReLU'
+//   g_csr[b,k,h] = g_k;  da_dst[b,i,h] = sum_k g_k
+template <int VW, int L>
+__global__ void __launch_bounds__(kWarps * 32)
+    gat_bwd_dst_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                       const float* __restrict__ z, const float* __restrict__ a_src,
+                       const float* __restrict__ a_dst, const float* __restrict__ alpha_csr,
+                       const float* __restrict__ dout, float* __restrict__ g_csr, float* __restrict__ da_dst,
+                       int64_t N, int64_t nnz, int H, int C, int concat, float slope) {
+  using V = W<VW>;
+  constexpr int S = 32 / L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane & (L - 1), slot = lane / L;
+  const int64_t i = (int64_t)blockIdx.x * kWarps + warp;
+  const int64_t b = blockIdx.y;
+  if (i >= N) return;
+  const int32_t beg = rowptr[i], end = rowptr[i + 1];
+  const int HC = H * C, Cout = concat ? HC : C;
+  const int64_t nb = b * N;
+  const float* zb = z + nb * HC;
+  const int words = (C + VW - 1) / VW;
+  const int nchunks = (words + L - 1) / L;
+  const float hs = concat ? 1.f : 1.f / (float)H;
+
+  for (int h = 0; h < H; ++h) {
+    // dalpha_k for every entry of the row (S entries at a time), parked in g_csr
+    for (int32_t base = beg; base < end; base += S) {
+      const int32_t k = base + slot;
+      const bool valid = k < end;
+      const int32_t c = valid ? col[k] : 0;
+      float d = 0.f;
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int off = (chunk * L + gl) * VW;
+        if (valid && off < C) {
+          const typename V::T dv = V::load(dout + (nb + i) * Cout + (concat ? h * C : 0) + off);
+          d += V::dot(dv, V::load(zb + (int64_t)c * HC + h * C + off));
+        }
+      }
+#pragma unroll
+      for (int o = L / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (valid && gl == 0) g_csr[(b * nnz + k) * H + h] = d * hs;
+    }
+    __syncwarp();
+    const float adi = a_dst[(nb + i) * H + h];
+    float t = 0.f;
+    for (int32_t k = beg + lane; k < end; k += 32)
+      t += alpha_csr[(b * nnz + k) * H + h] * g_csr[(b * nnz + k) * H + h];
+    t = warp_sum(t);
+    float gs = 0.f;
+    for (int32_t k = beg + lane; k < end; k += 32) {
+      const int64_t idx = (b * nnz + k) * H + h;
+      const float pre = a_src[(nb + col[k]) * H + h] + adi;
+      const float g = alpha_csr[idx] * (g_csr[idx] - t) * (pre > 0.f ? 1.f : slope);
+      g_csr[idx] = g;
+      gs += g;
+    }
+    gs = warp_sum(gs);
+    if (lane == 0) da_dst[(nb + i) * H + h] = gs;
+    __syncwarp();
+  }
+}
+
+// Backward pass 2, one warp per (sample, sender j), sender-grouped CSR:
+//   da_src[b,j,h] = sum_k g_k ;  dz[b,j,h,:] = sum_k alpha_k do_h(i_k) + da_src att_src[h] + da_dst att_dst[h]
+template <int VW, int L>
+__global__ void __launch_bounds__(kWarps * 32)
+    gat_bwd_src_kernel(const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
+                       const int32_t* __restrict__ t2r, const float* __restrict__ alpha_csr,
+                       const float* __restrict__ g_csr, const float* __restrict__ att_src,
+                       const float* __restrict__ att_dst, const float* __restrict__ dout,
+                       const float* __restrict__ da_dst, float* __restrict__ da_src, float* __restrict__ dz,
+                       int64_t N, int64_t nnz, int H, int C, int concat) {
+  using V = W<VW>;
+  constexpr int S = 32 / L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane & (L - 1), slot = lane / L;
+  const int64_t jn = (int64_t)blockIdx.x * kWarps + warp;
+  const int64_t b = blockIdx.y;
+  if (jn >= N) return;
+  const int32_t beg = rowptr_t[jn], end = rowptr_t[jn + 1];
+  const int HC = H * C, Cout = concat ? HC : C;
+  const int64_t nb = b * N;
+  const int words = (C + VW - 1) / VW;
+  const int nchunks = (words + L - 1) / L;
+  const float hs = concat ? 1.f : 1.f / (float)H;
+
+  for (int h = 0; h < H; ++h) {
+    float gs = 0.f;
+    for (int32_t k = beg + lane; k < end; k += 32) gs += g_csr[(b * nnz + t2r[k]) * H + h];
+    gs = warp_sum(gs);
+    if (lane == 0) da_src[(nb + jn) * H + h] = gs;
+    const float dad = da_dst[(nb + jn) * H + h];
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      const int off = (chunk * L + gl) * VW;
+      const bool live = off < C;
+      typename V::T acc = V::zero();
+      for (int32_t base = beg; base < end; base += 32) {
+        const int32_t k = base + lane;
+        const int n = min(32, end - base);
+        int32_t i_reg = 0;
+        float a_reg = 0.f;
+        if (k < end) {
+          i_reg = col_t[k];
+          a_reg = alpha_csr[(b * nnz + t2r[k]) * H + h] * hs;
+        }
+        for (int jj = 0; jj < n; jj += S) {
+          const int j = jj + slot;
+          const int src = j < n ? j : 0;
+          const int32_t ii = __shfl_sync(0xffffffffu, i_reg, src);
+          const float a = __shfl_sync(0xffffffffu, a_reg, src);
+          if (j < n && live) V::fma(acc, a, V::load(dout + (nb + ii) * Cout + (concat ? h * C : 0) + off));
+        }
+      }
+#pragma unroll
+      for (int o = L; o < 32; o <<= 1) acc = V::xor_add(acc, o);
+      if (live && slot == 0) {
+        V::fma(acc, gs, V::load(att_src + h * C + off));
+        V::fma(acc, dad, V::load(att_dst + h * C + off));
+        V::store(dz + (nb + jn) * HC + h * C + off, acc);
+      }
+    }
+  }
+}
+
+// part[blk][0][hc] = sum_rows da_src[row,h] z[row,hc];  part[blk][1][hc] likewise with da_dst
+__global__ void gat_datt_partial_kernel(const float* __restrict__ z, const float* __restrict__ da_src,
+                                        const float* __restrict__ da_dst, float* __restrict__ part, int64_t rows,
+                                        int H, int C, int64_t rows_per_block) {
+  __shared__ float sm[2][8][33];
+  const int HC = H * C;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  for (int c0 = 0; c0 < HC; c0 += 32) {
+    const int c = c0 + threadIdx.x;
+    float s = 0.f, d = 0.f;
+    if (c < HC) {
+      const int h = c / C;
+      for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+        const float v = z[r * HC + c];
+        s = fmaf(da_src[r * H + h], v, s);
+        d = fmaf(da_dst[r * H + h], v, d);
+      }
+    }
+    sm[0][threadIdx.y][threadIdx.x] = s;
+    sm[1][threadIdx.y][threadIdx.x] = d;
+    __syncthreads();
+    if (threadIdx.y < 2 && c < HC) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += sm[threadIdx.y][k][threadIdx.x];
+      part[((int64_t)blockIdx.x * 2 + threadIdx.y) * HC + c] = t;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void reduce2_kernel(const float* __restrict__ part, int nblk, int n, float* __restrict__ out0,
+                               float* __restrict__ out1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n) return;
+  float s = 0.f;
+  for (int k = 0; k < nblk; ++k) s += part[(int64_t)k * 2 * n + i];
+  if (i < n) out0[i] = s;
+  else out1[i - n] = s;
+}
+
+__global__ void prune_flags_kernel(const float* __restrict__ alpha, int64_t nnz, float thr,
+                                   int32_t* __restrict__ flag) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p < nnz) flag[p] = alpha[p] >= thr;
+}
+
+__global__ void prune_compact_kernel(const int64_t* __restrict__ ei, int64_t ei_stride,
+                                     const int32_t* __restrict__ flag, const int32_t* __restrict__ pos,
+                                     int64_t nnz, int64_t* __restrict__ out, int64_t out_stride,
+                                     int32_t* __restrict__ count) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p == 0) *count = pos[nnz];
+  if (p < nnz && flag[p]) {
+    out[pos[p]] = ei[p];
+    out[out_stride + pos[p]] = ei[ei_stride + p];
+  }
+}
+
+struct Plan {
+  int nblk;
+  int64_t rows_per_block;
+};
+Plan rows_plan(int64_t rows) {
+  int64_t nblk = 4 * kNumSMs;
+  int64_t rpb = ceil_div(rows, nblk);
+  if (rpb < 8) rpb = 8;
+  nblk = ceil_div(rows, rpb);
+  if (nblk < 1) nblk = 1;
+  return {(int)nblk, rpb};
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int pick_l(int words) { return words <= 4 ? 4 : words <= 8 ? 8 : words <= 16 ? 16 : 32; }
+
+}  // namespace
+}  // namespace gcl
+
+using namespace gcl;
+
+#define GAT_DISPATCH(VWV, LV, KERNEL, ...)                                              \
+  do {                                                                                  \
+    if (VWV == 4) {                                                                     \
+      if (LV == 4) KERNEL<4, 4><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);              \
+      else if (LV == 8) KERNEL<4, 8><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);         \
+      else if (LV == 16) KERNEL<4, 16><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);       \
+      else KERNEL<4, 32><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);                     \
+    } else {                                                                            \
+      if (LV == 4) KERNEL<1, 4><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);              \
+      else if (LV == 8) KERNEL<1, 8><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);         \
+      else if (LV == 16) KERNEL<1, 16><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);       \
+      else KERNEL<1, 32><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);                     \
+    }                                                                                   \
+  } while (0)
+
+extern "C" int gcl_gat_scores_f32(const float* z, const float* att_src, const float* att_dst, float* a_src,
+                                  float* a_dst, int64_t rows, int64_t heads, int64_t c, void* stream) {
+  GCL_CHECK_ARG(z && att_src && att_dst && a_src && a_dst && rows >= 0 && heads > 0 && c > 0,
+                "gcl_gat_scores_f32: bad argument");
+  if (rows == 0) return GCL_OK;
+  gat_scores_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      z, att_src, att_dst, a_src, a_dst, rows, (int)heads, (int)c);
+  GCL_CHECK_LAUNCH("gcl_gat_scores_f32");
+  return GCL_OK;
+}
+
+extern "C" int gcl_gat_fwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* z,
+                               const float* a_src, const float* a_dst, const float* bias, float* out,
+                               float* alpha_csr, float* alpha_pyg, int64_t batch, int64_t n_nodes, int64_t nnz,
+                               int64_t heads, int64_t c, int concat, float negative_slope, void* stream) {
+  GCL_CHECK_ARG(rowptr && col && z && a_src && a_dst && out && alpha_csr, "gcl_gat_fwd_f32: null pointer argument");
+  GCL_CHECK_ARG(!alpha_pyg || perm, "gcl_gat_fwd_f32: alpha_pyg needs perm");
+  GCL_CHECK_ARG(batch >= 0 && batch <= 65535 && n_nodes >= 0 && nnz >= 0 && heads > 0 && c > 0,
+                "gcl_gat_fwd_f32: bad sizes");
+  if (batch == 0 || n_nodes == 0) return GCL_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int vw = (c % 4 == 0 && al16(z) && al16(out) && (!bias || al16(bias))) ? 4 : 1;
+  const int l = pick_l((int)ceil_div(c, vw));
+  dim3 grid((unsigned)ceil_div(n_nodes, kWarps), (unsigned)batch);
+  GAT_DISPATCH(vw, l, gat_fwd_kernel, rowptr, col, perm, z, a_src, a_dst, bias, out, alpha_csr, alpha_pyg, n_nodes,
+               nnz, (int)heads, (int)c, concat, negative_slope);
+  GCL_CHECK_LAUNCH("gcl_gat_fwd_f32");
+  return GCL_OK;
+}
+
+extern "C" int gcl_gat_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t,
+                               const int32_t* col_t, const int32_t* t2r, const float* z, const float* a_src,
+                               const float* a_dst, const float* alpha_csr, const float* att_src,
+                               const float* att_dst, const float* dout, float* g_csr, float* da_src, float* da_dst,
+                               float* dz, int64_t batch, int64_t n_nodes, int64_t nnz, int64_t heads, int64_t c,
+                               int concat, float negative_slope, void* stream) {
+  GCL_CHECK_ARG(rowptr && col && rowptr_t && col_t && t2r && z && a_src && a_dst && alpha_csr && att_src && att_dst &&
+                    dout && g_csr && da_src && da_dst && dz,
+                "gcl_gat_bwd_f32: null pointer argument");
+  GCL_CHECK_ARG(batch >= 0 && batch <= 65535 && n_nodes >= 0 && nnz >= 0 && heads > 0 && c > 0,
+                "gcl_gat_bwd_f32: bad sizes");
+  if (batch == 0 || n_nodes == 0) return GCL_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int vw = (c % 4 == 0 && al16(z) && al16(dout) && al16(dz) && al16(att_src) && al16(att_dst)) ? 4 : 1;
+  const int l = pick_l((int)ceil_div(c, vw));
+  dim3 grid((unsigned)ceil_div(n_nodes, kWarps), (unsigned)batch);
+  GAT_DISPATCH(vw, l, gat_bwd_dst_kernel, rowptr, col, z, a_src, a_dst, alpha_csr, dout, g_csr, da_dst, n_nodes, nnz,
+               (int)heads, (int)c, concat, negative_slope);
+  GCL_CHECK_LAUNCH("gcl_gat_bwd_f32(dst pass)");
+  GAT_DISPATCH(vw, l, gat_bwd_src_kernel, rowptr_t, col_t, t2r, alpha_csr, g_csr, att_src, att_dst, dout, da_dst,
+               da_src, dz, n_nodes, nnz, (int)heads, (int)c, concat);
+  GCL_CHECK_LAUNCH("gcl_gat_bwd_f32(src pass)");
+  return GCL_OK;
+}
+
+extern "C" size_t gcl_gat_datt_workspace_bytes(int64_t rows, int64_t heads, int64_t c) {
+  if (rows < 0 || heads <= 0 || c <= 0) return 0;
+  return (size_t)rows_plan(rows).nblk * 2 * (size_t)(heads * c) * sizeof(float) + 256;
+}
+
+extern "C" int gcl_gat_datt_f32(const float* z, const float* da_src, const float* da_dst, float* datt_src,
+                                float* datt_dst, int64_t rows, int64_t heads, int64_t c, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  GCL_CHECK_ARG(z && da_src && da_dst && datt_src && datt_dst && workspace && rows >= 0 && heads > 0 && c > 0,
+                "gcl_gat_datt_f32: bad argument");
+  if (workspace_bytes < gcl_gat_datt_workspace_bytes(rows, heads, c)) {
+    set_error("gcl_gat_datt_f32: workspace too small");
+    return GCL_ERR_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int HC = (int)(heads * c);
+  if (rows == 0) {
+    cudaMemsetAsync(datt_src, 0, sizeof(float) * HC, s);
+    cudaMemsetAsync(datt_dst, 0, sizeof(float) * HC, s);
+    return GCL_OK;
+  }
+  Plan pl = rows_plan(rows);
+  float* part = static_cast<float*>(workspace);
+  gat_datt_partial_kernel<<<pl.nblk, dim3(32, 8), 0, s>>>(z, da_src, da_dst, part, rows, (int)heads, (int)c,
+                                                          pl.rows_per_block);
+  GCL_CHECK_LAUNCH("gcl_gat_datt_f32(partial)");
+  reduce2_kernel<<<(unsigned)ceil_div(2 * HC, 256), 256, 0, s>>>(part, pl.nblk, HC, datt_src, datt_dst);
+  GCL_CHECK_LAUNCH("gcl_gat_datt_f32(reduce)");
+  return GCL_OK;
+}
+
+extern "C" size_t gcl_edge_prune_workspace_bytes(int64_t nnz) {
+  if (nnz < 0) return 0;
+  return 2 * (((size_t)(nnz + 1) * sizeof(int32_t) + 255) & ~size_t(255)) + 256;
+}
+
+extern "C" int gcl_edge_prune(const int64_t* ei_pyg, const float* alpha_pyg, int64_t nnz, int64_t ei_stride,
+                              float threshold, int64_t* ei_kept, int64_t kept_stride, int32_t* count_out,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  GCL_CHECK_ARG(ei_pyg && alpha_pyg && ei_kept && count_out && workspace && nnz >= 0, "gcl_edge_prune: bad argument");
+  if (workspace_bytes < gcl_edge_prune_workspace_bytes(nnz)) {
+    set_error("gcl_edge_prune: workspace too small");
+    return GCL_ERR_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int32_t* flag = static_cast<int32_t*>(workspace);
+  int32_t* pos = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) +
+                                            (((size_t)(nnz + 1) * sizeof(int32_t) + 255) & ~size_t(255)));
+  if (nnz > 0) {
+    prune_flags_kernel<<<(unsigned)ceil_div(nnz, 256), 256, 0, s>>>(alpha_pyg, nnz, threshold, flag);
+    GCL_CHECK_LAUNCH("gcl_edge_prune(flags)");
+  }
+  scan_exclusive_kernel<<<1, kScanThreads, 0, s>>>(flag, pos, nnz, nullptr);
+  GCL_CHECK_LAUNCH("gcl_edge_prune(scan)");
+  prune_compact_kernel<<<(unsigned)ceil_div(nnz + 1, 256), 256, 0, s>>>(ei_pyg, ei_stride, flag, pos, nnz, ei_kept,
+                                                                        kept_stride, count_out);
+  GCL_CHECK_LAUNCH("gcl_edge_prune(compact)");
+  return GCL_OK;
+}

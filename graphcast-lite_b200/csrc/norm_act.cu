@@ -1,0 +1,293 @@
+// PReLU and LayerNorm(mode="node"), forward and backward, fp32, deterministic reductions.
+//   torch.nn.PReLU (one slope)             /root/reference/src/models.py:78,90,159,316
+//   torch_geometric.nn.LayerNorm(mode=node) /root/reference/src/models.py:103,370  == F.layer_norm over C
+#include "common.cuh"
+
+namespace gcl {
+namespace {
+
+constexpr int kEwThreads = 256;
+constexpr int kEwMaxBlocks = 8 * kNumSMs;
+
+__global__ void prelu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ slope,
+                                 float* __restrict__ y, int64_t n) {
+  const float a = __ldg(slope);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) y[i] = prelu_f(x[i], a);
+}
+
+// dx = dy * (x > 0 ? 1 : a); part[blk] = sum over the block's elements of dy * x * [x <= 0]
+// Each block owns a CONTIGUOUS element range so the summation order is fixed.
+__global__ void prelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                 const float* __restrict__ slope, float* __restrict__ dx,
+                                 float* __restrict__ part, int64_t n, int64_t per_block) {
+  __shared__ float sm[kEwThreads / 32];
+  const float a = __ldg(slope);
+  const int64_t beg = (int64_t)blockIdx.x * per_block, end = min(n, beg + per_block);
+  float s = 0.f;
+  for (int64_t i = beg + threadIdx.x; i < end; i += kEwThreads) {
+    const float xv = x[i], g = dy[i];
+    const bool pos = xv > 0.f;
+    dx[i] = pos ? g : a * g;
+    s += pos ? 0.f : g * xv;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kEwThreads / 32; ++k) t += sm[k];
+    part[blockIdx.x] = t;
+  }
+}
+
+__global__ void sum_partials_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
+  // one warp, fixed order: lane-strided partial sums then a shuffle tree
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) s += part[i];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) *out = s;
+}
+
+// ---- LayerNorm over the last dim, one warp per row, row cached in registers (C <= 32 * NPER) -------
+template <int NPER>
+__global__ void __launch_bounds__(256)
+    layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ mean_out,
+                         float* __restrict__ rstd_out, int64_t rows, int C, float eps) {
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * C;
+  float v[NPER];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NPER; ++j) {
+    const int c = lane + 32 * j;
+    v[j] = c < C ? xr[c] : 0.f;
+    s += v[j];
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NPER; ++j) {
+    const int c = lane + 32 * j;
+    const float d = c < C ? v[j] - mean : 0.f;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  float* yr = y + row * C;
+#pragma unroll
+  for (int j = 0; j < NPER; ++j) {
+    const int c = lane + 32 * j;
+    if (c < C) {
+      float o = (v[j] - mean) * rstd;
+      if (gamma) o = o * __ldg(gamma + c) + __ldg(beta + c);
+      yr[c] = o;
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma.
+// Each block owns a contiguous row range; its column partials of dgamma / dbeta go to
+// part[blk][0][c] / part[blk][1][c] (fixed-order reduction afterwards).
+template <int NPER>
+__global__ void __launch_bounds__(256)
+    layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                         const float* __restrict__ gamma, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, float* __restrict__ dx, float* __restrict__ part,
+                         int64_t rows, int C, int64_t rows_per_block) {
+  extern __shared__ float sm[];  // [8 warps][2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float dg[NPER], db[NPER], gm[NPER];
+#pragma unroll
+  for (int j = 0; j < NPER; ++j) {
+    dg[j] = db[j] = 0.f;
+    const int c = lane + 32 * j;
+    gm[j] = (gamma && c < C) ? __ldg(gamma + c) : 1.f;
+  }
+  for (int64_t row = r0 + warp; row < r1; row += 8) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NPER], g[NPER];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPER; ++j) {
+      const int c = lane + 32 * j;
+      const bool in = c < C;
+      const float d = in ? dy[row * C + c] : 0.f;
+      xh[j] = in ? (x[row * C + c] - mu) * rs : 0.f;
+      g[j] = d * gm[j];
+      dg[j] += d * xh[j];
+      db[j] += d;
+      s1 += g[j];
+      s2 += g[j] * xh[j];
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+    for (int j = 0; j < NPER; ++j) {
+      const int c = lane + 32 * j;
+      if (c < C) dx[row * C + c] = rs * (g[j] - s1 - xh[j] * s2);
+    }
+  }
+  if (part == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < NPER; ++j) {
+    const int c = lane + 32 * j;
+    if (c < C) {
+      sm[(warp * 2 + 0) * C + c] = dg[j];
+      sm[(warp * 2 + 1) * C + c] = db[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w * 2 * C + i];
+    part[(int64_t)blockIdx.x * 2 * C + i] = t;
+  }
+}
+
+__global__ void reduce_cols_kernel(const float* __restrict__ part, int nblk, int n, float* __restrict__ out0,
+                                   float* __restrict__ out1, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < nblk; ++k) s += part[(int64_t)k * n + i];
+  if (i < C) out0[i] = s;
+  else out1[i - C] = s;
+}
+
+struct LnPlan {
+  int nblk;
+  int64_t rows_per_block;
+};
+LnPlan ln_plan(int64_t rows) {
+  int64_t nblk = 4 * kNumSMs;
+  int64_t rpb = ceil_div(rows, nblk);
+  if (rpb < 8) rpb = 8;
+  nblk = ceil_div(rows, rpb);
+  if (nblk < 1) nblk = 1;
+  return {(int)nblk, rpb};
+}
+
+int ew_blocks(int64_t n) {
+  int64_t b = ceil_div(n, kEwThreads);
+  return (int)(b < 1 ? 1 : (b > kEwMaxBlocks ? kEwMaxBlocks : b));
+}
+
+}  // namespace
+}  // namespace gcl
+
+using namespace gcl;
+
+extern "C" int gcl_prelu_fwd_f32(const float* x, const float* slope, float* y, int64_t n, void* stream) {
+  GCL_CHECK_ARG(x && slope && y && n >= 0, "gcl_prelu_fwd_f32: bad argument");
+  if (n == 0) return GCL_OK;
+  prelu_fwd_kernel<<<ew_blocks(n), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, slope, y, n);
+  GCL_CHECK_LAUNCH("gcl_prelu_fwd_f32");
+  return GCL_OK;
+}
+
+extern "C" size_t gcl_prelu_bwd_workspace_bytes(int64_t n) {
+  (void)n;
+  return (size_t)kEwMaxBlocks * sizeof(float) + 256;
+}
+
+extern "C" int gcl_prelu_bwd_f32(const float* dy, const float* x, const float* slope, float* dx, float* dslope,
+                                 int64_t n, void* workspace, size_t workspace_bytes, void* stream) {
+  GCL_CHECK_ARG(dy && x && slope && dx && dslope && workspace && n >= 0, "gcl_prelu_bwd_f32: bad argument");
+  if (workspace_bytes < gcl_prelu_bwd_workspace_bytes(n)) {
+    set_error("gcl_prelu_bwd_f32: workspace too small");
+    return GCL_ERR_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n == 0) {
+    cudaMemsetAsync(dslope, 0, sizeof(float), s);
+    return GCL_OK;
+  }
+  const int nblk = ew_blocks(n);
+  const int64_t per_block = ceil_div(n, nblk);
+  float* part = static_cast<float*>(workspace);
+  prelu_bwd_kernel<<<nblk, kEwThreads, 0, s>>>(dy, x, slope, dx, part, n, per_block);
+  GCL_CHECK_LAUNCH("gcl_prelu_bwd_f32");
+  sum_partials_kernel<<<1, 32, 0, s>>>(part, nblk, dslope);
+  GCL_CHECK_LAUNCH("gcl_prelu_bwd_f32(reduce)");
+  return GCL_OK;
+}
+
+extern "C" int gcl_layernorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                                     float* rstd, int64_t rows, int64_t c, float eps, void* stream) {
+  GCL_CHECK_ARG(x && y && rows >= 0 && c > 0, "gcl_layernorm_fwd_f32: bad argument");
+  GCL_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "gcl_layernorm_fwd_f32: gamma and beta go together");
+  if (c > 1024) {
+    set_error("gcl_layernorm_fwd_f32: channels %lld > 1024 unsupported", (long long)c);
+    return GCL_ERR_UNSUPPORTED;
+  }
+  if (rows == 0) return GCL_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)ceil_div(rows * 32, 256);
+  if (c <= 128) layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, (int)c, eps);
+  else if (c <= 256) layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, (int)c, eps);
+  else layernorm_fwd_kernel<32><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, (int)c, eps);
+  GCL_CHECK_LAUNCH("gcl_layernorm_fwd_f32");
+  return GCL_OK;
+}
+
+extern "C" size_t gcl_layernorm_bwd_workspace_bytes(int64_t rows, int64_t c) {
+  if (rows < 0 || c <= 0) return 0;
+  return (size_t)ln_plan(rows).nblk * 2 * (size_t)c * sizeof(float) + 256;
+}
+
+extern "C" int gcl_layernorm_bwd_f32(const float* dy, const float* x, const float* gamma, const float* mean,
+                                     const float* rstd, float* dx, float* dgamma, float* dbeta, int64_t rows,
+                                     int64_t c, void* workspace, size_t workspace_bytes, void* stream) {
+  GCL_CHECK_ARG(dy && x && mean && rstd && dx && rows >= 0 && c > 0, "gcl_layernorm_bwd_f32: bad argument");
+  GCL_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "gcl_layernorm_bwd_f32: dgamma and dbeta go together");
+  if (c > 1024) {
+    set_error("gcl_layernorm_bwd_f32: channels %lld > 1024 unsupported", (long long)c);
+    return GCL_ERR_UNSUPPORTED;
+  }
+  const bool want_params = dgamma != nullptr;
+  if (want_params && (!workspace || workspace_bytes < gcl_layernorm_bwd_workspace_bytes(rows, c))) {
+    set_error("gcl_layernorm_bwd_f32: workspace too small");
+    return GCL_ERR_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rows == 0) {
+    if (want_params) {
+      cudaMemsetAsync(dgamma, 0, sizeof(float) * c, s);
+      cudaMemsetAsync(dbeta, 0, sizeof(float) * c, s);
+    }
+    return GCL_OK;
+  }
+  LnPlan pl = ln_plan(rows);
+  float* part = want_params ? static_cast<float*>(workspace) : nullptr;
+  const size_t smem = (size_t)8 * 2 * c * sizeof(float);
+  const int C = (int)c;
+  if (c <= 128)
+    layernorm_bwd_kernel<4><<<pl.nblk, 256, smem, s>>>(dy, x, gamma, mean, rstd, dx, part, rows, C, pl.rows_per_block);
+  else if (c <= 256)
+    layernorm_bwd_kernel<8><<<pl.nblk, 256, smem, s>>>(dy, x, gamma, mean, rstd, dx, part, rows, C, pl.rows_per_block);
+  else {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+      if (e != cudaSuccess) return fail_cuda(e, "gcl_layernorm_bwd_f32(smem attr)");
+    }
+    layernorm_bwd_kernel<32><<<pl.nblk, 256, smem, s>>>(dy, x, gamma, mean, rstd, dx, part, rows, C,
+                                                        pl.rows_per_block);
+  }
+  GCL_CHECK_LAUNCH("gcl_layernorm_bwd_f32");
+  if (want_params) {
+    reduce_cols_kernel<<<(unsigned)ceil_div(2 * c, 256), 256, 0, s>>>(part, pl.nblk, 2 * C, dgamma, dbeta, C);
+    GCL_CHECK_LAUNCH("gcl_layernorm_bwd_f32(reduce)");
+  }
+  return GCL_OK;
+}

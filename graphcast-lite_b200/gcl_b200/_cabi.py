@@ -1,0 +1,85 @@
+"""ctypes binding of libgcl_b200.so (the C ABI declared in include/gcl_b200.h).
+
+There is deliberately NO fallback: if the library is missing or a call fails, a RuntimeError is
+raised (BASELINE.json north_star: "no CPU fallback").  The GIL is released during every call.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_LIB_NAME = "libgcl_b200.so"
+_lib = None
+
+P, I64, I32, F32, SZ = c_void_p, c_int64, c_int, c_float, c_size_t
+
+# name -> (restype, argtypes); mirrors include/gcl_b200.h one to one.
+_PROTOS = {
+    "gcl_version": (c_int, []),
+    "gcl_last_error": (c_char_p, []),
+    "gcl_csr_workspace_bytes": (SZ, [I64, I64]),
+    "gcl_csr_build": (c_int, [P, P, I64, I64, I32, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
+    "gcl_csr_weights": (c_int, [P, P, P, P, P, I64, I64, I32, P, P, P, P]),
+    "gcl_spmm_f32": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, P, P, P, P]),
+    "gcl_linear_fwd_f32": (c_int, [P, P, P, P, I64, I64, I64, P, P, P, P]),
+    "gcl_linear_bwd_dx_f32": (c_int, [P, P, P, I64, I64, I64, P]),
+    "gcl_linear_bwd_dw_workspace_bytes": (SZ, [I64, I64, I64]),
+    "gcl_linear_bwd_dw_f32": (c_int, [P, P, P, P, I64, I64, I64, P, SZ, P]),
+    "gcl_colsum_workspace_bytes": (SZ, [I64, I64]),
+    "gcl_colsum_f32": (c_int, [P, P, I64, I64, P, SZ, P]),
+    "gcl_prelu_fwd_f32": (c_int, [P, P, P, I64, P]),
+    "gcl_prelu_bwd_workspace_bytes": (SZ, [I64]),
+    "gcl_prelu_bwd_f32": (c_int, [P, P, P, P, P, I64, P, SZ, P]),
+    "gcl_layernorm_fwd_f32": (c_int, [P, P, P, P, P, P, I64, I64, F32, P]),
+    "gcl_layernorm_bwd_workspace_bytes": (SZ, [I64, I64]),
+    "gcl_layernorm_bwd_f32": (c_int, [P, P, P, P, P, P, P, P, I64, I64, P, SZ, P]),
+    "gcl_gat_scores_f32": (c_int, [P, P, P, P, P, I64, I64, I64, P]),
+    "gcl_gat_fwd_f32": (c_int, [P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I32, F32, P]),
+    "gcl_gat_bwd_f32": (c_int, [P] * 16 + [I64, I64, I64, I64, I64, I32, F32, P]),
+    "gcl_gat_datt_workspace_bytes": (SZ, [I64, I64, I64]),
+    "gcl_gat_datt_f32": (c_int, [P, P, P, P, P, I64, I64, I64, P, SZ, P]),
+    "gcl_edge_prune_workspace_bytes": (SZ, [I64]),
+    "gcl_edge_prune": (c_int, [P, P, I64, I64, F32, P, I64, P, P, SZ, P]),
+    "gcl_assemble_input_f32": (c_int, [P, P, P, P, I64, I64, I64, I64, I64, P]),
+    "gcl_wmse_workspace_bytes": (SZ, [I64, I64, I64]),
+    "gcl_wmse_f32": (c_int, [P, P, I64, P, I64, P, F32, P, P, P, I32, F32, I64, I64, I64, P, SZ, P]),
+    "gcl_adam_f32": (c_int, [P, P, P, P, I64, F32, F32, F32, F32, F32, P, P]),
+}
+
+ABI_VERSION = 1
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+def load():
+    """Load (once) and return the CDLL.  Raises RuntimeError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"gcl_b200: {path} not found -- build it with graphcast-lite_b200/csrc/build.sh "
+            "(python -c 'import __graft_entry__ as g; g.build()').  There is no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+        fn.restype, fn.argtypes = res, args
+    if lib.gcl_version() != ABI_VERSION:
+        raise RuntimeError(f"gcl_b200: ABI version {lib.gcl_version()} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def exported_names():
+    return sorted(_PROTOS)
+
+
+def last_error() -> str:
+    return load().gcl_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")

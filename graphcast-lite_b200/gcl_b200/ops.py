@@ -1,0 +1,348 @@
+"""torch.autograd.Function custom ops over the gcl_b200 C ABI (fp32, deterministic, CUDA only).
+
+Every op checks its inputs and raises instead of falling back to PyTorch/CPU.  Tensors are
+[B, N, C] (B samples on one shared graph) or the reference's [N, C].
+"""
+from typing import Optional
+
+import torch
+
+from . import _cabi
+from .graph import CSRGraph, NORM_GCN, NORM_MEAN, NORM_NONE  # noqa: F401
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"gcl_b200: {name} must be a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"gcl_b200: {name} is on {t.device}; the kernels are CUDA (sm_100a) only, no CPU fallback")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"gcl_b200: {name} has dtype {t.dtype}; this build computes in float32")
+    return t.contiguous()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _call(name: str, *args) -> None:
+    lib = _cabi.load()
+    _cabi.check(getattr(lib, name)(*args), name)
+
+
+def _as3(x: torch.Tensor):
+    """[N, C] -> ([1, N, C], squeeze?)"""
+    if x.dim() == 2:
+        return x.unsqueeze(0), True
+    if x.dim() == 3:
+        return x, False
+    raise ValueError(f"gcl_b200: node features must be [N, C] or [B, N, C], got {tuple(x.shape)}")
+
+
+# ------------------------------------------------------------------------------------------- raw calls
+def spmm_raw(rowptr, col, w, x3, n_out, bias=None, slope=None, want_z=False):
+    B, n_in, C = x3.shape
+    out = torch.empty((B, n_out, C), dtype=torch.float32, device=x3.device)
+    z = torch.empty_like(out) if want_z else None
+    with torch.cuda.device(x3.device):
+        _call("gcl_spmm_f32", _p(rowptr), _p(col), _p(w), _p(x3), _p(out), B, n_out, C, n_in * C, n_out * C,
+              _p(bias), _p(slope), _p(z), _stream())
+    return out, z
+
+
+def colsum_raw(x2):
+    R, C = x2.shape
+    out = torch.empty(C, dtype=torch.float32, device=x2.device)
+    lib = _cabi.load()
+    nb = lib.gcl_colsum_workspace_bytes(R, C)
+    ws = _ws(nb, x2.device)
+    with torch.cuda.device(x2.device):
+        _call("gcl_colsum_f32", _p(x2), _p(out), R, C, _p(ws), nb, _stream())
+    return out
+
+
+def prelu_bwd_raw(dy, z, slope):
+    dx = torch.empty_like(dy)
+    dslope = torch.empty(1, dtype=torch.float32, device=dy.device)
+    lib = _cabi.load()
+    n = dy.numel()
+    nb = lib.gcl_prelu_bwd_workspace_bytes(n)
+    ws = _ws(nb, dy.device)
+    with torch.cuda.device(dy.device):
+        _call("gcl_prelu_bwd_f32", _p(dy), _p(z), _p(slope), _p(dx), _p(dslope), n, _p(ws), nb, _stream())
+    return dx, dslope
+
+
+def linear_fwd_raw(x2, W, bias=None, slope=None, want_z=False):
+    R, cin = x2.shape
+    cout = W.shape[0]
+    y = torch.empty((R, cout), dtype=torch.float32, device=x2.device)
+    z = torch.empty_like(y) if want_z else None
+    wt = torch.empty(cin * cout, dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        _call("gcl_linear_fwd_f32", _p(x2), _p(W), _p(bias), _p(y), R, cin, cout, _p(slope), _p(z), _p(wt), _stream())
+    return y, z
+
+
+def linear_bwd_dx_raw(dy2, W):
+    R, cout = dy2.shape
+    cin = W.shape[1]
+    dx = torch.empty((R, cin), dtype=torch.float32, device=dy2.device)
+    with torch.cuda.device(dy2.device):
+        _call("gcl_linear_bwd_dx_f32", _p(dy2), _p(W), _p(dx), R, cin, cout, _stream())
+    return dx
+
+
+def linear_bwd_dw_raw(dy2, x2, want_bias):
+    R, cout = dy2.shape
+    cin = x2.shape[1]
+    dW = torch.empty((cout, cin), dtype=torch.float32, device=dy2.device)
+    db = torch.empty(cout, dtype=torch.float32, device=dy2.device) if want_bias else None
+    lib = _cabi.load()
+    nb = lib.gcl_linear_bwd_dw_workspace_bytes(R, cin, cout)
+    ws = _ws(nb, dy2.device)
+    with torch.cuda.device(dy2.device):
+        _call("gcl_linear_bwd_dw_f32", _p(dy2), _p(x2), _p(dW), _p(db), R, cin, cout, _p(ws), nb, _stream())
+    return dW, db
+
+
+# ------------------------------------------------------------------------------------------- autograd
+class _Aggregate(torch.autograd.Function):
+    """out = prelu?( A_w x + bias ), A_w = CSR with per-entry weights of `kind`.  Backward uses the
+    sender-grouped CSR (A_w^T), so it is a gather too -- no atomics."""
+
+    @staticmethod
+    def forward(ctx, x, bias, slope, graph: CSRGraph, kind: int):
+        x3, squeeze = _as3(_chk(x, "x"))
+        if x3.shape[1] != graph.num_nodes:
+            raise ValueError(f"gcl_b200: x has {x3.shape[1]} nodes, graph has {graph.num_nodes}")
+        bias_c = _chk(bias, "bias") if bias is not None else None
+        slope_c = _chk(slope, "slope") if slope is not None else None
+        w, _ = graph.weights(kind)
+        need_z = slope_c is not None and any(ctx.needs_input_grad[:3])
+        out, z = spmm_raw(graph.rowptr, graph.col, w, x3, graph.num_nodes, bias_c, slope_c, need_z)
+        ctx.graph, ctx.kind, ctx.squeeze = graph, kind, squeeze
+        ctx.has_bias, ctx.has_slope = bias is not None, slope is not None
+        ctx.save_for_backward(z, slope_c)
+        return out.squeeze(0) if squeeze else out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, slope = ctx.saved_tensors
+        g = ctx.graph
+        d3, _ = _as3(_chk(dout, "grad_out"))
+        dslope = None
+        if ctx.has_slope:
+            d3, dslope = prelu_bwd_raw(d3, z, slope)
+            dslope = dslope.view_as(slope)
+        dbias = colsum_raw(d3.view(-1, d3.shape[-1])) if ctx.has_bias and ctx.needs_input_grad[1] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, wt = g.weights(ctx.kind)
+            dx, _ = spmm_raw(g.rowptr_t, g.col_t, wt, d3, g.num_nodes)
+            if ctx.squeeze:
+                dx = dx.squeeze(0)
+        return dx, dbias, (dslope if ctx.has_slope and ctx.needs_input_grad[2] else None), None, None
+
+
+def aggregate(x, graph: CSRGraph, kind: int, bias=None, prelu_slope=None):
+    return _Aggregate.apply(x, bias, prelu_slope, graph, kind)
+
+
+class _Linear(torch.autograd.Function):
+    """y = prelu?( x W^T + b ) over the last dim."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, slope):
+        xc, Wc = _chk(x, "x"), _chk(W, "weight")
+        if xc.shape[-1] != Wc.shape[1]:
+            raise ValueError(f"gcl_b200: linear got x[..., {xc.shape[-1]}] and weight {tuple(Wc.shape)}")
+        bias_c = _chk(bias, "bias") if bias is not None else None
+        slope_c = _chk(slope, "slope") if slope is not None else None
+        x2 = xc.view(-1, xc.shape[-1])
+        need_z = slope_c is not None and any(ctx.needs_input_grad)
+        y, z = linear_fwd_raw(x2, Wc, bias_c, slope_c, need_z)
+        ctx.has_bias, ctx.has_slope = bias is not None, slope is not None
+        ctx.save_for_backward(x2, Wc, z, slope_c)
+        return y.view(*xc.shape[:-1], Wc.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W, z, slope = ctx.saved_tensors
+        d2 = _chk(dy, "grad_out").view(-1, W.shape[0])
+        dslope = None
+        if ctx.has_slope:
+            d2, dslope = prelu_bwd_raw(d2, z, slope)
+            dslope = dslope.view_as(slope)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = linear_bwd_dx_raw(d2, W).view(*dy.shape[:-1], W.shape[1])
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dW, db = linear_bwd_dw_raw(d2, x2, ctx.has_bias)
+        return dx, dW, (db if ctx.has_bias else None), (dslope if ctx.has_slope else None)
+
+
+def linear(x, weight, bias=None, prelu_slope=None):
+    return _Linear.apply(x, weight, bias, prelu_slope)
+
+
+class _PReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        xc, sc = _chk(x, "x"), _chk(slope, "slope")
+        if sc.numel() != 1:
+            raise RuntimeError("gcl_b200: PReLU with one shared slope only (reference: nn.PReLU())")
+        y = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            _call("gcl_prelu_fwd_f32", _p(xc), _p(sc), _p(y), xc.numel(), _stream())
+        ctx.save_for_backward(xc, sc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, slope = ctx.saved_tensors
+        dx, ds = prelu_bwd_raw(_chk(dy, "grad_out"), x, slope)
+        return dx, ds.view_as(slope)
+
+
+def prelu(x, slope):
+    return _PReLU.apply(x, slope)
+
+
+class _LayerNorm(torch.autograd.Function):
+    """F.layer_norm over the last dim (torch_geometric LayerNorm(mode='node'))."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        xc = _chk(x, "x")
+        C = xc.shape[-1]
+        x2 = xc.view(-1, C)
+        g = _chk(gamma, "weight") if gamma is not None else None
+        b = _chk(beta, "bias") if beta is not None else None
+        R = x2.shape[0]
+        y = torch.empty_like(x2)
+        mean = torch.empty(R, dtype=torch.float32, device=xc.device)
+        rstd = torch.empty(R, dtype=torch.float32, device=xc.device)
+        with torch.cuda.device(xc.device):
+            _call("gcl_layernorm_fwd_f32", _p(x2), _p(g), _p(b), _p(y), _p(mean), _p(rstd), R, C, float(eps),
+                  _stream())
+        ctx.affine = gamma is not None
+        ctx.save_for_backward(x2, g, mean, rstd)
+        return y.view_as(xc)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, g, mean, rstd = ctx.saved_tensors
+        R, C = x2.shape
+        d2 = _chk(dy, "grad_out").view(R, C)
+        dx = torch.empty_like(x2)
+        dg = torch.empty(C, dtype=torch.float32, device=x2.device) if ctx.affine else None
+        db = torch.empty(C, dtype=torch.float32, device=x2.device) if ctx.affine else None
+        lib = _cabi.load()
+        nb = lib.gcl_layernorm_bwd_workspace_bytes(R, C)
+        ws = _ws(nb, x2.device)
+        with torch.cuda.device(x2.device):
+            _call("gcl_layernorm_bwd_f32", _p(d2), _p(x2), _p(g), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db), R, C,
+                  _p(ws), nb, _stream())
+        return dx.view_as(dy), dg, db, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    return _LayerNorm.apply(x, weight, bias, eps)
+
+
+class _GAT(torch.autograd.Function):
+    """Attention logits + LeakyReLU + segment softmax + weighted aggregation + head mean/concat + bias.
+    z is the already-transformed [B, N, H*C] (or [N, H*C]) feature matrix."""
+
+    @staticmethod
+    def forward(ctx, z, att_src, att_dst, bias, graph: CSRGraph, heads, concat, slope, want_alpha):
+        z3, squeeze = _as3(_chk(z, "z"))
+        B, N, HC = z3.shape
+        H = int(heads)
+        C = HC // H
+        a_s, a_d = _chk(att_src, "att_src").view(-1), _chk(att_dst, "att_dst").view(-1)
+        bias_c = _chk(bias, "bias") if bias is not None else None
+        dev = z3.device
+        asrc = torch.empty((B, N, H), dtype=torch.float32, device=dev)
+        adst = torch.empty((B, N, H), dtype=torch.float32, device=dev)
+        nnz = graph.nnz
+        cout = HC if concat else C
+        out = torch.empty((B, N, cout), dtype=torch.float32, device=dev)
+        alpha = torch.empty((B, max(nnz, 1), H), dtype=torch.float32, device=dev)
+        alpha_pyg = torch.empty((B, max(nnz, 1), H), dtype=torch.float32, device=dev) if want_alpha else None
+        with torch.cuda.device(dev):
+            _call("gcl_gat_scores_f32", _p(z3), _p(a_s), _p(a_d), _p(asrc), _p(adst), B * N, H, C, _stream())
+            _call("gcl_gat_fwd_f32", _p(graph.rowptr), _p(graph.col), _p(graph.perm), _p(z3), _p(asrc), _p(adst),
+                  _p(bias_c), _p(out), _p(alpha), _p(alpha_pyg), B, N, nnz, H, C, int(bool(concat)), float(slope),
+                  _stream())
+        ctx.graph, ctx.H, ctx.C, ctx.concat, ctx.slope = graph, H, C, bool(concat), float(slope)
+        ctx.squeeze, ctx.has_bias = squeeze, bias is not None
+        ctx.save_for_backward(z3, asrc, adst, alpha, a_s, a_d)
+        if squeeze:
+            out = out.squeeze(0)
+        if want_alpha:
+            ap = alpha_pyg[:, :nnz]
+            ctx.mark_non_differentiable(ap)
+            return out, (ap.squeeze(0) if squeeze else ap)
+        return out, None
+
+    @staticmethod
+    def backward(ctx, dout, _dalpha=None):
+        z3, asrc, adst, alpha, a_s, a_d = ctx.saved_tensors
+        g = ctx.graph
+        B, N, HC = z3.shape
+        H, C = ctx.H, ctx.C
+        d3, _ = _as3(_chk(dout, "grad_out"))
+        dev = z3.device
+        gbuf = torch.empty_like(alpha)
+        da_s = torch.empty_like(asrc)
+        da_d = torch.empty_like(adst)
+        dz = torch.empty_like(z3)
+        datt_s = torch.empty(HC, dtype=torch.float32, device=dev)
+        datt_d = torch.empty(HC, dtype=torch.float32, device=dev)
+        lib = _cabi.load()
+        nb = lib.gcl_gat_datt_workspace_bytes(B * N, H, C)
+        ws = _ws(nb, dev)
+        with torch.cuda.device(dev):
+            _call("gcl_gat_bwd_f32", _p(g.rowptr), _p(g.col), _p(g.rowptr_t), _p(g.col_t), _p(g.t2r), _p(z3),
+                  _p(asrc), _p(adst), _p(alpha), _p(a_s), _p(a_d), _p(d3), _p(gbuf), _p(da_s), _p(da_d), _p(dz),
+                  B, N, g.nnz, H, C, int(ctx.concat), ctx.slope, _stream())
+            _call("gcl_gat_datt_f32", _p(z3), _p(da_s), _p(da_d), _p(datt_s), _p(datt_d), B * N, H, C, _p(ws), nb,
+                  _stream())
+        dbias = colsum_raw(d3.view(-1, d3.shape[-1])) if ctx.has_bias else None
+        if ctx.squeeze:
+            dz = dz.squeeze(0)
+        return dz, datt_s.view(1, H, C), datt_d.view(1, H, C), dbias, None, None, None, None, None
+
+
+def gat_attend(z, att_src, att_dst, bias, graph, heads, concat, negative_slope, want_alpha=False):
+    return _GAT.apply(z, att_src, att_dst, bias, graph, heads, concat, negative_slope, want_alpha)
+
+
+def edge_prune(ei_pyg: torch.Tensor, alpha_pyg: torch.Tensor, threshold: float) -> torch.Tensor:
+    """SparseGATConv pruning (models.py:140-149): edges with alpha >= threshold, order preserved."""
+    if not ei_pyg.is_cuda or not alpha_pyg.is_cuda:
+        raise RuntimeError("gcl_b200: edge_prune needs CUDA tensors; no CPU fallback")
+    a = alpha_pyg.detach().reshape(-1).to(torch.float32).contiguous()
+    nnz = a.numel()
+    if ei_pyg.shape[1] != nnz:
+        raise ValueError("edge_prune: one attention value per edge expected (heads=1)")
+    ei = ei_pyg if ei_pyg.stride(1) == 1 else ei_pyg.contiguous()
+    out = torch.empty((2, max(nnz, 1)), dtype=torch.int64, device=ei.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=ei.device)
+    lib = _cabi.load()
+    nb = lib.gcl_edge_prune_workspace_bytes(nnz)
+    ws = _ws(nb, ei.device)
+    with torch.cuda.device(ei.device):
+        _call("gcl_edge_prune", _p(ei), _p(a), nnz, ei.stride(0), float(threshold), _p(out), out.stride(0),
+              _p(cnt), _p(ws), nb, _stream())
+    return out[:, : int(cnt.item())].contiguous()

@@ -1,0 +1,213 @@
+/* gcl_b200 -- C ABI of the B200-native (sm_100a) message-passing kernels that replace the
+ * torch_geometric arithmetic behind graphcast-lite's encode-process-decode hot path.
+ *
+ * The reference (ArturKKK/graphcast-lite) is pure Python and binds this path by IMPORT:
+ *   /root/reference/src/models.py:21   from torch_geometric.nn import GCNConv, SimpleConv, GATConv, LayerNorm
+ *   /root/reference/src/models.py:24   from torch_geometric.utils import dense_to_sparse, softmax
+ *   /root/reference/src/models.py:220  from torch_geometric.utils import scatter
+ * so the reference-side binding is the ctypes stub shown in INTEGRATION.md; every entry point below
+ * names the reference/PyG call it stands in for.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller (PyTorch),
+ *     never retained after return; the library allocates nothing on the device;
+ *   - all functions only ENQUEUE on `stream` (a cudaStream_t passed as void*), never synchronise,
+ *     and are CUDA-graph capturable;
+ *   - return 0 on success, <0 on error (GCL_ERR_*); gcl_last_error() gives the thread-local text;
+ *   - node-feature tensors are row-major fp32 [B, N, C] (B samples over one shared graph; B = 1 is the
+ *     reference's layout [N, C]); `*_bstride` is the element distance between samples;
+ *   - index arrays produced by gcl_csr_build are int32; edge_index is PyG's int64 [2, E]
+ *     (row 0 = sender, row 1 = receiver).
+ *   - results are deterministic: no floating-point atomics anywhere.
+ */
+#ifndef GCL_B200_H_
+#define GCL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCL_OK 0
+#define GCL_ERR_BAD_ARG (-1)
+#define GCL_ERR_UNSUPPORTED (-2)
+#define GCL_ERR_CUDA (-3)
+#define GCL_ERR_WORKSPACE (-4)
+
+/* ABI version (bumped on any signature change). */
+int gcl_version(void);
+/* Thread-local text of the last error returned on this host thread ("" if none). */
+const char* gcl_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  graph -> CSR.  Replaces, per call of GCNConv/GATConv/SimpleConv.forward, PyG's
+ *     add_remaining_self_loops / remove_self_loops + add_self_loops / gcn_norm
+ *     (torch_geometric/nn/conv/gcn_conv.py:gcn_norm; used via models.py:419,425,414) -- done ONCE per
+ *     edge_index here and cached by the caller.
+ *
+ * mode: GCL_CSR_RAW   keep the edge list as it is                (SimpleConv, models.py:309)
+ *       GCL_CSR_LOOPS drop i->i edges, append one i->i per node  (GCNConv / GATConv)
+ * The "PyG edge order" is: kept edges in input order, then (LOOPS) nodes 0..N-1.  nnz = kept (+ N).
+ *
+ * Outputs (all device):
+ *   ei_out   int64 [2, nnz_cap]  PyG-order edge list incl. loops (what GATConv returns with
+ *                                return_attention_weights=True); nnz_cap = E + N (LOOPS) or E (RAW)
+ *   w_pyg    fp32  [nnz_cap]     PyG-order raw edge weight (edge_weight or 1; loop = existing loop's
+ *                                weight or 1)                      -- nullable
+ *   rowptr   int32 [N+1], col int32 [nnz_cap], perm int32 [nnz_cap]
+ *            receiver-grouped CSR: entries of row i = senders of i, ascending PyG position;
+ *            perm[k] = PyG position of CSR entry k
+ *   rowptr_t, col_t, perm_t      the same grouped by SENDER (col_t = receivers), for backward
+ *   t2r      int32 [nnz_cap]     CSR position of sender-grouped entry k (t2r[k] = inv_perm[perm_t[k]])
+ *   nnz_out  int32 [1]
+ * edge_weight: nullable fp32 [E].
+ */
+#define GCL_CSR_RAW 0
+#define GCL_CSR_LOOPS 1
+size_t gcl_csr_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+int gcl_csr_build(const int64_t* edge_index, const float* edge_weight, int64_t num_edges,
+                  int64_t num_nodes, int mode, int64_t* ei_out, float* w_pyg, int32_t* rowptr,
+                  int32_t* col, int32_t* perm, int32_t* rowptr_t, int32_t* col_t, int32_t* perm_t,
+                  int32_t* t2r, int32_t* nnz_out, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* Per-entry aggregation weights in CSR order (and the same values in sender-grouped order):
+ *   GCL_NORM_GCN   w = d^-1/2[src] * w_pyg * d^-1/2[dst],  d[i] = sum of w_pyg over row i (inf -> 0)
+ *                  (gcn_norm, improved=False)
+ *   GCL_NORM_MEAN  w = w_pyg / max(count[dst], 1)           (SimpleConv(aggr="mean"), models.py:309)
+ *   GCL_NORM_NONE  w = w_pyg
+ * w_pyg nullable (= all ones).  Deterministic (row sums are sequential).
+ */
+#define GCL_NORM_NONE 0
+#define GCL_NORM_GCN 1
+#define GCL_NORM_MEAN 2
+int gcl_csr_weights(const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                    const int32_t* t2r, const float* w_pyg, int64_t num_nodes, int64_t nnz_cap,
+                    int kind, float* deg_inv_sqrt /* nullable [N] */, float* w_csr,
+                    float* w_csr_t /* nullable */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2/K3/K6  deterministic segmented SpMM:  out[b,i,:] = epi( sum_{k in row i} w[k] * x[b,col[k],:] )
+ *   forward of GCNConv.propagate / SimpleConv (index_select + mul + scatter_add_ in PyG) with the
+ *   receiver-grouped CSR; their backward with the sender-grouped CSR (no atomics).
+ *   epi: (+ bias[C]) then optional PReLU (slope = *prelu_slope, device scalar; models.py:316 shares
+ *   one nn.PReLU per GraphLayer).  z_out (nullable) receives the value before PReLU.
+ *   w nullable (= 1).  x and out must not alias.
+ */
+int gcl_spmm_f32(const int32_t* rowptr, const int32_t* col, const float* w, const float* x,
+                 float* out, int64_t batch, int64_t n_rows_out, int64_t channels, int64_t x_bstride,
+                 int64_t out_bstride, const float* bias, const float* prelu_slope, float* z_out,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7  node-wise dense transform  y = act(x W^T + b)  (torch.nn.Linear in MLP, models.py:74-98, and the
+ *   bias-free `lin` inside GCNConv/GATConv).  x [R, Cin], W [Cout, Cin], y [R, Cout], fp32 FFMA with
+ *   fp32 accumulation.  bias / prelu_slope / z_out nullable (z_out = value before PReLU).
+ *   wt_scratch: device scratch of Cin*Cout floats (holds W^T).
+ */
+int gcl_linear_fwd_f32(const float* x, const float* W, const float* bias, float* y, int64_t rows,
+                       int64_t c_in, int64_t c_out, const float* prelu_slope, float* z_out,
+                       float* wt_scratch, void* stream);
+/* dx[R, Cin] = dy[R, Cout] W */
+int gcl_linear_bwd_dx_f32(const float* dy, const float* W, float* dx, int64_t rows, int64_t c_in,
+                          int64_t c_out, void* stream);
+/* dW[Cout, Cin] = dy^T x ; dbias[Cout] = column sums of dy (nullable).  Deterministic split over rows. */
+size_t gcl_linear_bwd_dw_workspace_bytes(int64_t rows, int64_t c_in, int64_t c_out);
+int gcl_linear_bwd_dw_f32(const float* dy, const float* x, float* dW, float* dbias, int64_t rows,
+                          int64_t c_in, int64_t c_out, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* Column sums of a [R, C] matrix (bias gradients), deterministic.  workspace >= gcl_colsum_workspace_bytes. */
+size_t gcl_colsum_workspace_bytes(int64_t rows, int64_t cols);
+int gcl_colsum_f32(const float* x, float* out, int64_t rows, int64_t cols, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* PReLU (torch.nn.PReLU with one slope; models.py:78,159):  y = x > 0 ? x : a x */
+int gcl_prelu_fwd_f32(const float* x, const float* slope, float* y, int64_t n, void* stream);
+/* dx = dy * (x > 0 ? 1 : a);  dslope[1] = sum(dy * x * [x <= 0]).  Deterministic. */
+size_t gcl_prelu_bwd_workspace_bytes(int64_t n);
+int gcl_prelu_bwd_f32(const float* dy, const float* x, const float* slope, float* dx, float* dslope,
+                      int64_t n, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a6  torch_geometric.nn.LayerNorm (models.py:103,370).
+ *   mode "node" = F.layer_norm(x, (C,), gamma, beta, eps), the mode of every BASELINE config.
+ *   (mode "graph" is composed on the host from these primitives; see gcl_b200/nn.)
+ *   x, y [R, C]; mean/rstd [R] saved for backward; gamma/beta nullable together (affine=False).
+ */
+int gcl_layernorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y,
+                          float* mean, float* rstd, int64_t rows, int64_t c, float eps,
+                          void* stream);
+size_t gcl_layernorm_bwd_workspace_bytes(int64_t rows, int64_t c);
+int gcl_layernorm_bwd_f32(const float* dy, const float* x, const float* gamma, const float* mean,
+                          const float* rstd, float* dx, float* dgamma, float* dbeta, int64_t rows,
+                          int64_t c, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4/K5  GATConv (models.py:336-357) / SparseGATConv (models.py:112-151) after the dense transform:
+ *   z [B, N, H, C] = lin(x);  a_s = <z, att_src>, a_d = <z, att_dst>   [B, N, H]
+ *   e_ij = LeakyReLU_slope(a_s[j] + a_d[i]);  alpha = exp(e - max_i) / (sum_i exp(.) + 1e-16)
+ *   out[b,i,:] = (concat ? [o_1..o_H] : mean_h o_h) + bias,  o_h = sum_j alpha_ijh z[b,j,h,:]
+ * gcl_gat_fwd_f32 does logits + LeakyReLU + segment softmax + aggregation in ONE kernel.
+ *   alpha_csr  fp32 [B, nnz, H]  attention in CSR order (kept for backward)
+ *   alpha_pyg  nullable fp32 [B, nnz, H] attention in PyG edge order (return_attention_weights=True)
+ */
+int gcl_gat_scores_f32(const float* z, const float* att_src, const float* att_dst, float* a_src,
+                       float* a_dst, int64_t rows /* B*N */, int64_t heads, int64_t c, void* stream);
+int gcl_gat_fwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* z,
+                    const float* a_src, const float* a_dst, const float* bias, float* out,
+                    float* alpha_csr, float* alpha_pyg, int64_t batch, int64_t n_nodes, int64_t nnz,
+                    int64_t heads, int64_t c, int concat, float negative_slope, void* stream);
+/* Backward.  Pass 1 (receiver-grouped): g = d(pre-LeakyReLU logit) per entry, da_dst.
+ * Pass 2 (sender-grouped): dz = sum_i alpha_ij do_i + da_src att_src + da_dst att_dst, da_src.
+ *   dout [B, N, Cout]; g_csr scratch [B, nnz, H]; da_src/da_dst [B, N, H] (outputs, also needed for
+ *   d att_src = sum da_src z, computed by the caller with gcl_gat_datt_f32).
+ */
+int gcl_gat_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t,
+                    const int32_t* col_t, const int32_t* t2r, const float* z, const float* a_src,
+                    const float* a_dst, const float* alpha_csr, const float* att_src,
+                    const float* att_dst, const float* dout, float* g_csr, float* da_src,
+                    float* da_dst, float* dz, int64_t batch, int64_t n_nodes, int64_t nnz,
+                    int64_t heads, int64_t c, int concat, float negative_slope, void* stream);
+/* datt_src[h,c] = sum_{b,n} da_src[b,n,h] z[b,n,h,c]  (same for dst).  Deterministic. */
+size_t gcl_gat_datt_workspace_bytes(int64_t rows, int64_t heads, int64_t c);
+int gcl_gat_datt_f32(const float* z, const float* da_src, const float* da_dst, float* datt_src,
+                     float* datt_dst, int64_t rows, int64_t heads, int64_t c, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* SparseGATConv pruning (models.py:138-149): keep PyG-order edges with alpha >= threshold.
+ * Writes the compacted int64 [2, kept] list to ei_kept (capacity nnz) and kept to count_out[1]. */
+size_t gcl_edge_prune_workspace_bytes(int64_t nnz);
+int gcl_edge_prune(const int64_t* ei_pyg, const float* alpha_pyg, int64_t nnz, int64_t ei_stride,
+                   float threshold, int64_t* ei_kept, int64_t kept_stride, int32_t* count_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a9/a14  glue of one forecast / training step (models.py:776-806, train.py:85-102,203-213; Adam).
+ */
+/* enc_in[b, n, :] = n < G ? [x[b,n,:TF], grid_static[n,:S]] : [0..0, mesh_static[n-G,:S]] */
+int gcl_assemble_input_f32(const float* x, const float* grid_static, const float* mesh_static,
+                           float* enc_in, int64_t batch, int64_t n_grid, int64_t n_mesh, int64_t tf,
+                           int64_t s, void* stream);
+/* Residual + latitude-weighted MSE (train.py:85-102, 203-213), forward and gradient in one pass:
+ *   out = (x_last ? x_last : 0) + delta;  loss = scale * inv_wsum * sum(w (out - y)^2),  w[b,g,c] = lat_w[g]
+ *   (lat_w nullable = 1; inv_wsum = 1 / sum of all weights, host-computed);
+ *   d_delta = scale * 2 w (out - y) * inv_wsum.   x_last / y rows have strides xl_stride / y_stride
+ *   (views into [.., steps, C]).  loss_out[1] is overwritten, or added to when `accumulate`;
+ *   out_state (nullable [B,G,C]) receives `out`; d_delta nullable. */
+size_t gcl_wmse_workspace_bytes(int64_t batch, int64_t n_grid, int64_t c);
+int gcl_wmse_f32(const float* delta, const float* x_last, int64_t xl_stride, const float* y,
+                 int64_t y_stride, const float* lat_w, float inv_wsum, float* out_state,
+                 float* d_delta, float* loss_out, int accumulate, float scale, int64_t batch,
+                 int64_t n_grid, int64_t c, void* workspace, size_t workspace_bytes, void* stream);
+/* torch.optim.Adam (main.py:212; betas/eps defaults, weight_decay 0) over one flat fp32 buffer.
+ * step_count: device int32[1], incremented by the kernel (graph-replay safe). grad_scale multiplies g. */
+int gcl_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, float grad_scale,
+                 int32_t* step_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCL_B200_H_ */
