@@ -21,9 +21,12 @@ int fail_cuda(cudaError_t e, const char* what);
     }                                            \
   } while (0)
 
+void count_launch();
+
 // After a launch: pick up launch-configuration errors without synchronising the stream.
 #define GCL_CHECK_LAUNCH(what)                                   \
   do {                                                           \
+    ::gcl::count_launch();                                       \
     cudaError_t e__ = cudaPeekAtLastError();                     \
     if (e__ != cudaSuccess) {                                    \
       cudaGetLastError();                                        \

@@ -8,7 +8,7 @@ Host side of the C ABI in include/gcl_b200.h:
   gcl_b200.graph   device CSR builder + cache
 There is no CPU fallback: CPU tensors or a missing libgcl_b200.so raise.
 """
-from . import _cabi, graph, nn, ops, utils, workloads  # noqa: F401
+from . import _cabi, graph, graphs_build, model, nn, ops, train, utils, workloads  # noqa: F401
 
 __version__ = "0.1.0"
 

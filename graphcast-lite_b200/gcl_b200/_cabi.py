@@ -16,6 +16,7 @@ P, I64, I32, F32, SZ = c_void_p, c_int64, c_int, c_float, c_size_t
 _PROTOS = {
     "gcl_version": (c_int, []),
     "gcl_last_error": (c_char_p, []),
+    "gcl_launch_count": (ctypes.c_longlong, []),
     "gcl_csr_workspace_bytes": (SZ, [I64, I64]),
     "gcl_csr_build": (c_int, [P, P, I64, I64, I32, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
     "gcl_csr_weights": (c_int, [P, P, P, P, P, I64, I64, I32, P, P, P, P]),
@@ -39,6 +40,10 @@ _PROTOS = {
     "gcl_gat_datt_f32": (c_int, [P, P, P, P, P, I64, I64, I64, P, SZ, P]),
     "gcl_edge_prune_workspace_bytes": (SZ, [I64]),
     "gcl_edge_prune": (c_int, [P, P, I64, I64, F32, P, I64, P, P, SZ, P]),
+    "gcl_radius_query_workspace_bytes": (SZ, [I64]),
+    "gcl_radius_query_count": (c_int, [P, P, I64, I64, ctypes.c_double, P, P, SZ, P]),
+    "gcl_radius_query_fill": (c_int, [P, P, I64, I64, ctypes.c_double, P, P, I64, I64, P]),
+    "gcl_closest_face": (c_int, [P, P, P, I64, I64, I64, ctypes.c_double, P, P]),
     "gcl_assemble_input_f32": (c_int, [P, P, P, P, I64, I64, I64, I64, I64, P]),
     "gcl_wmse_workspace_bytes": (SZ, [I64, I64, I64]),
     "gcl_wmse_f32": (c_int, [P, P, I64, P, I64, P, F32, P, P, P, I32, F32, I64, I64, I64, P, SZ, P]),

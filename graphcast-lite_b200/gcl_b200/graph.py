@@ -73,11 +73,15 @@ class CSRGraph:
         self.nnz = int(self.nnz_dev.item())  # one-time sync at graph build
         self.max_in_degree = int((self.rowptr[1:] - self.rowptr[:-1]).max()) if N > 0 else 0
         self._weights = {}
+        self._ei_view = None
 
     @property
     def edge_index_with_loops(self) -> torch.Tensor:
-        """PyG-order [2, nnz] int64 edge list (kept edges, then one loop per node)."""
-        return self.ei_pyg[:, : self.nnz]
+        """PyG-order [2, nnz] int64 edge list (kept edges, then one loop per node).  Always the same
+        tensor object, so feeding it back (SparseGAT, models.py:846) hits the graph cache."""
+        if self._ei_view is None:
+            self._ei_view = self.ei_pyg[:, : self.nnz]
+        return self._ei_view
 
     def weights(self, kind: int):
         """(w_csr, w_csr_t) for NORM_GCN / NORM_MEAN / NORM_NONE; None for unit weights."""
@@ -124,6 +128,11 @@ class GraphCache:
             del self._d[key]  # address reused by another tensor
         g = CSRGraph(edge_index, num_nodes, mode, edge_weight)
         self._d[key] = (weakref.ref(edge_index), g)
+        if mode == CSR_LOOPS and edge_weight is None:
+            # dropping and re-adding the loops of g's own PyG-order list reproduces it: alias it to g
+            v = g.edge_index_with_loops
+            vkey = (v.data_ptr(), tuple(v.shape), v._version, int(num_nodes), mode, None, v.device.index)
+            self._d[vkey] = (weakref.ref(v), g)
         while len(self._d) > self.capacity:
             self._d.popitem(last=False)
         return g

@@ -1,0 +1,237 @@
+"""Batched, fused mirror of the reference's encode-process-decode model.
+
+Same module tree and parameter names as /root/reference/src/models.py (MLP :54-109, GraphLayer
+:289-440, Model :443-473, WeatherPrediction :476-874), so a reference ``state_dict`` loads unchanged
+(the InteractionNet-only buffer ``_processing_edge_features`` is ignored), but
+
+  * inputs may be [B, G, T*F]: B forecast samples share the three static graphs (the reference is
+    batch-1 only, models.py:822);
+  * Linear+bias+PReLU and aggregate+bias+PReLU are single kernels, graphs are device CSR built once,
+    the encoder input is assembled by one kernel instead of zeros + 3 cats (models.py:776-806).
+
+Product graph, InteractionNet and regional meshes are out of scope.
+"""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _cabi, ops
+from .graph import CSR_LOOPS, CSR_RAW, GLOBAL_CACHE, NORM_GCN, NORM_MEAN
+from .graphs_build import ModelGraphs
+from .nn import GATConv, GCNConv, LayerNorm, SimpleConv
+
+
+def _truthy(v) -> bool:
+    return v is True or (isinstance(v, str) and v.lower() == "true")
+
+
+class MLP(nn.Module):
+    """Linear(+PReLU) stack (+ LayerNorm); the attribute is called ``MLP`` as in the reference."""
+
+    def __init__(self, cfg: dict, input_dim: int):
+        super().__init__()
+        self.MLP = nn.ModuleList()
+        last = input_dim
+        for h in (cfg.get("mlp_hidden_dims") or []):
+            self.MLP.extend([nn.Linear(last, h), nn.PReLU()])
+            last = h
+        self.MLP.append(nn.Linear(last, cfg["output_dim"]))
+        if _truthy(cfg.get("use_layer_norm")):
+            self.MLP.append(LayerNorm(cfg["output_dim"], mode=cfg.get("layer_norm_mode") or "graph"))
+
+    def forward(self, X):
+        mods = list(self.MLP)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Linear):
+                nxt = mods[i + 1] if i + 1 < len(mods) else None
+                if isinstance(nxt, nn.PReLU):
+                    X = ops.linear(X, m.weight, m.bias, nxt.weight)   # fused Linear + bias + PReLU
+                    i += 2
+                    continue
+                X = ops.linear(X, m.weight, m.bias)
+            elif isinstance(m, nn.PReLU):
+                X = ops.prelu(X, m.weight)
+            else:
+                X = m(X)
+            i += 1
+        return X
+
+
+class SparseGATConv(GATConv):
+    """models.py:112-151.  For B > 1 the pruning decision uses the batch-mean attention."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=False, dropout=0.0, bias=True, **kw):
+        super().__init__(in_channels, out_channels, heads, concat=concat, dropout=dropout, bias=bias, **kw)
+
+    def forward(self, x, edge_index, attention_threshold=0.0, **kwargs):
+        batch_num = kwargs.get("batch_num", 1)
+        out, (edge_index, att) = super().forward(x, edge_index, return_attention_weights=True)
+        if att.dim() == 3:
+            att = att.mean(dim=0)
+        att = att.squeeze()
+        if batch_num == 0:
+            edge_index = ops.edge_prune(edge_index, att, float(attention_threshold))
+        return out, (edge_index, att)
+
+
+class GraphLayer(nn.Module):
+    def __init__(self, cfg: dict, input_dim: int):
+        super().__init__()
+        self.layer_type = cfg["layer_type"]
+        if self.layer_type == "simple_conv":
+            self.output_dim = input_dim
+            self.layers = SimpleConv(aggr="mean")
+            return
+        if self.layer_type not in ("conv_gcn", "conv_gat", "sparse_gat"):
+            raise NotImplementedError(f"gcl_b200: layer type {self.layer_type!r} is out of scope (SURVEY.md 8)")
+        act = cfg.get("activation") or "prelu"
+        if act != "prelu":
+            raise NotImplementedError(f"gcl_b200: activation {act!r} (v2 configs) is out of scope")
+        self.activation = nn.PReLU()
+        self.output_dim = cfg["output_dim"]
+        self.layers = nn.ModuleList()
+        hid = list(cfg.get("hidden_dims") or [])
+        if self.layer_type == "sparse_gat":
+            self.layers.append(SparseGATConv(input_dim, self.output_dim, heads=cfg["gat_props"]["num_heads"],
+                                             concat=False))
+        else:
+            def conv(i, o):
+                if self.layer_type == "conv_gcn":
+                    return GCNConv(i, o)
+                return GATConv(i, o, heads=cfg["gat_props"]["num_heads"], concat=False)
+            dims = [input_dim] + hid
+            for i in range(len(hid)):
+                self.layers.append(conv(dims[i], dims[i + 1]))
+                self.layers.append(self.activation)      # ONE shared PReLU, appended several times (models.py:316)
+            self.layers.append(conv(dims[-1], self.output_dim))
+        if _truthy(cfg.get("use_layer_norm")):
+            self.layers.append(LayerNorm(self.output_dim, mode=cfg.get("layer_norm_mode") or "graph"))
+
+    def forward(self, X, edge_index, attention_threshold=0.0, **kwargs):
+        if self.layer_type == "simple_conv":
+            return self.layers(x=X, edge_index=edge_index)
+        if self.layer_type == "sparse_gat":
+            for layer in self.layers:
+                if type(layer) is SparseGATConv:
+                    X, (edge_index, _) = layer.forward(X, edge_index, attention_threshold, **kwargs)
+                else:
+                    X = layer(X)
+            return X, edge_index
+        mods = list(self.layers)
+        n = X.size(-2)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            fuse = isinstance(nxt, nn.PReLU)
+            if type(m) is GCNConv:
+                g = GLOBAL_CACHE.get(edge_index, n, CSR_LOOPS)
+                h = ops.linear(X, m.lin.weight)
+                X = ops.aggregate(h, g, NORM_GCN, m.bias, nxt.weight if fuse else None)  # + bias + PReLU fused
+                i += 2 if fuse else 1
+            elif type(m) is GATConv:
+                X = m(X, edge_index)
+                i += 1
+            elif isinstance(m, nn.PReLU):
+                X = ops.prelu(X, m.weight)
+                i += 1
+            else:
+                X = m(X)
+                i += 1
+        return X
+
+
+class Model(nn.Module):
+    def __init__(self, cfg: dict, input_dim: int):
+        super().__init__()
+        self.mlp = MLP(cfg["mlp"], input_dim) if cfg.get("mlp") else None
+        gin = cfg["mlp"]["output_dim"] if cfg.get("mlp") else input_dim
+        self.graph_layer = GraphLayer(cfg["gcn"], gin)
+        self.output_dim = self.graph_layer.output_dim
+
+    def forward(self, X, edge_index, attention_threshold=0.0, **kwargs):
+        if self.mlp is not None:
+            X = self.mlp(X)
+        return self.graph_layer(X=X, edge_index=edge_index, attention_threshold=attention_threshold, **kwargs)
+
+
+class _AssembleInput(torch.autograd.Function):
+    """[B,G,TF] -> [B,G+M,TF+S]: grid rows get their static features appended, mesh rows are
+    zeros + static features (models.py:776-806), written by one kernel."""
+
+    @staticmethod
+    def forward(ctx, x, grid_static, mesh_static):
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise RuntimeError("gcl_b200: model input must be a float32 CUDA tensor; no CPU fallback")
+        x = x.contiguous()
+        B, G, TF = x.shape
+        M, S = mesh_static.shape
+        out = torch.empty((B, G + M, TF + S), dtype=torch.float32, device=x.device)
+        lib = _cabi.load()
+        with torch.cuda.device(x.device):
+            _cabi.check(lib.gcl_assemble_input_f32(x.data_ptr(), grid_static.data_ptr(), mesh_static.data_ptr(),
+                                                   out.data_ptr(), B, G, M, TF, S,
+                                                   torch.cuda.current_stream().cuda_stream),
+                        "gcl_assemble_input_f32")
+        ctx.G, ctx.TF = G, TF
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        return d[:, : ctx.G, : ctx.TF].contiguous(), None, None
+
+
+class WeatherPrediction(nn.Module):
+    """cfg = {"graph": ..., "pipeline": ..., "data": ...} in the reference's config.json schema
+    (see gcl_b200.workloads).  forward(X [B,G,T*F] | [G,T*F]) -> [B,G,F_out] | [G,F_out]."""
+
+    def __init__(self, cfg: dict, nlat: int, nlon: int, device="cuda:0", graphs: Optional[ModelGraphs] = None):
+        super().__init__()
+        if cfg["pipeline"].get("product_graph"):
+            raise NotImplementedError("gcl_b200: the product graph is out of scope (SURVEY.md 8)")
+        self.device = torch.device(device)
+        g = graphs or ModelGraphs(nlat, nlon, cfg["graph"]["mesh_levels"], cfg["graph"]["grid2mesh_radius_query"],
+                                  self.device)
+        self.graphs = g
+        self._num_grid_nodes, self._num_mesh_nodes = g.num_grid, g.num_mesh
+        self.obs_window = cfg["data"]["obs_window_used"]
+        self.num_features = cfg["data"]["num_features_used"]
+        self.total_feature_size = self.obs_window * self.num_features
+        # plain attributes, not buffers: like the reference they stay out of the state_dict (models.py:597-601)
+        self.encoding_graph, self.processing_graph, self.decoding_graph = (
+            g.encoding_graph, g.processing_graph, g.decoding_graph)
+        self.init_grid_features, self.init_mesh_features = g.init_grid_features, g.init_mesh_features
+        pipe = cfg["pipeline"]
+        self.using_sparse_gat = pipe["processor"]["gcn"]["layer_type"] == "sparse_gat"
+        self.encoder = Model(pipe["encoder"], self.total_feature_size + self.init_grid_features.shape[1])
+        self.processor = Model(pipe["processor"], self.encoder.output_dim)
+        self.decoder = Model(pipe["decoder"], self.processor.output_dim)
+        self.to(self.device)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        sd = {k: v for k, v in state_dict.items() if k != "_processing_edge_features"}
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    def forward(self, X: torch.Tensor, attention_threshold=0.0, **kwargs):
+        squeeze = False
+        if X.dim() == 2:
+            X, squeeze = X.unsqueeze(0), True
+        elif X.dim() == 3 and X.size(0) == 1:
+            squeeze = True                       # the reference returns [G, F] for its batch of one
+        G = self._num_grid_nodes
+        enc_in = _AssembleInput.apply(X, self.init_grid_features, self.init_mesh_features)
+        enc = self.encoder(X=enc_in, edge_index=self.encoding_graph)
+        grid_lat, mesh_lat = enc[:, :G], enc[:, G:]
+        if self.using_sparse_gat:
+            proc, new_ei = self.processor(X=mesh_lat, edge_index=self.processing_graph,
+                                          attention_threshold=attention_threshold, **kwargs)
+            self.processing_graph = new_ei           # models.py:846
+        else:
+            proc = self.processor(X=mesh_lat, edge_index=self.processing_graph,
+                                  attention_threshold=attention_threshold)
+        dec = self.decoder(X=torch.cat((grid_lat, proc), dim=1), edge_index=self.decoding_graph)
+        out = dec[:, :G]
+        return out.squeeze(0) if squeeze else out

@@ -33,9 +33,39 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
-def _call(name: str, *args) -> None:
+class KernelProfiler:
+    """CUDA-event timing of every C-ABI call on the launching stream (bench.py's roofline numbers).
+    `nbytes` is the ALGORITHMIC traffic of the call (DESIGN.md / SURVEY.md 8d), not a counter."""
+
+    def __init__(self):
+        self.records = []   # (name, tag, nbytes, start, end)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, tag, nbytes, s, e in self.records:
+            a = agg.setdefault((name, tag), dict(calls=0, ms=0.0, bytes=0))
+            a["calls"] += 1
+            a["ms"] += s.elapsed_time(e)
+            a["bytes"] += nbytes
+        return agg
+
+
+PROFILER: Optional[KernelProfiler] = None
+
+
+def _call(name: str, *args, nbytes: int = 0, tag: str = "") -> None:
     lib = _cabi.load()
-    _cabi.check(getattr(lib, name)(*args), name)
+    fn = getattr(lib, name)
+    if PROFILER is None:
+        _cabi.check(fn(*args), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn(*args)
+    e.record()
+    PROFILER.records.append((name, tag, int(nbytes), s, e))
+    _cabi.check(rc, name)
 
 
 def _as3(x: torch.Tensor):
@@ -53,8 +83,10 @@ def spmm_raw(rowptr, col, w, x3, n_out, bias=None, slope=None, want_z=False):
     out = torch.empty((B, n_out, C), dtype=torch.float32, device=x3.device)
     z = torch.empty_like(out) if want_z else None
     with torch.cuda.device(x3.device):
+        nnz = int(col.numel())
+        nbytes = 4 * B * C * (n_in + n_out * (2 if want_z else 1)) + nnz * (8 if w is not None else 4) + 4 * (n_out + 1)
         _call("gcl_spmm_f32", _p(rowptr), _p(col), _p(w), _p(x3), _p(out), B, n_out, C, n_in * C, n_out * C,
-              _p(bias), _p(slope), _p(z), _stream())
+              _p(bias), _p(slope), _p(z), _stream(), nbytes=nbytes, tag=f"N{n_out}xC{C}xB{B}")
     return out, z
 
 
@@ -65,7 +97,7 @@ def colsum_raw(x2):
     nb = lib.gcl_colsum_workspace_bytes(R, C)
     ws = _ws(nb, x2.device)
     with torch.cuda.device(x2.device):
-        _call("gcl_colsum_f32", _p(x2), _p(out), R, C, _p(ws), nb, _stream())
+        _call("gcl_colsum_f32", _p(x2), _p(out), R, C, _p(ws), nb, _stream(), nbytes=4 * R * C, tag=f"R{R}xC{C}")
     return out
 
 
@@ -77,7 +109,8 @@ def prelu_bwd_raw(dy, z, slope):
     nb = lib.gcl_prelu_bwd_workspace_bytes(n)
     ws = _ws(nb, dy.device)
     with torch.cuda.device(dy.device):
-        _call("gcl_prelu_bwd_f32", _p(dy), _p(z), _p(slope), _p(dx), _p(dslope), n, _p(ws), nb, _stream())
+        _call("gcl_prelu_bwd_f32", _p(dy), _p(z), _p(slope), _p(dx), _p(dslope), n, _p(ws), nb, _stream(),
+              nbytes=12 * n, tag=f"n{n}")
     return dx, dslope
 
 
@@ -88,7 +121,8 @@ def linear_fwd_raw(x2, W, bias=None, slope=None, want_z=False):
     z = torch.empty_like(y) if want_z else None
     wt = torch.empty(cin * cout, dtype=torch.float32, device=x2.device)
     with torch.cuda.device(x2.device):
-        _call("gcl_linear_fwd_f32", _p(x2), _p(W), _p(bias), _p(y), R, cin, cout, _p(slope), _p(z), _p(wt), _stream())
+        _call("gcl_linear_fwd_f32", _p(x2), _p(W), _p(bias), _p(y), R, cin, cout, _p(slope), _p(z), _p(wt), _stream(),
+              nbytes=4 * R * (cin + cout * (2 if want_z else 1)) + 4 * cin * cout, tag=f"R{R}x{cin}->{cout}")
     return y, z
 
 
@@ -97,7 +131,8 @@ def linear_bwd_dx_raw(dy2, W):
     cin = W.shape[1]
     dx = torch.empty((R, cin), dtype=torch.float32, device=dy2.device)
     with torch.cuda.device(dy2.device):
-        _call("gcl_linear_bwd_dx_f32", _p(dy2), _p(W), _p(dx), R, cin, cout, _stream())
+        _call("gcl_linear_bwd_dx_f32", _p(dy2), _p(W), _p(dx), R, cin, cout, _stream(),
+              nbytes=4 * R * (cin + cout) + 4 * cin * cout, tag=f"R{R}x{cout}->{cin}")
     return dx
 
 
@@ -110,7 +145,8 @@ def linear_bwd_dw_raw(dy2, x2, want_bias):
     nb = lib.gcl_linear_bwd_dw_workspace_bytes(R, cin, cout)
     ws = _ws(nb, dy2.device)
     with torch.cuda.device(dy2.device):
-        _call("gcl_linear_bwd_dw_f32", _p(dy2), _p(x2), _p(dW), _p(db), R, cin, cout, _p(ws), nb, _stream())
+        _call("gcl_linear_bwd_dw_f32", _p(dy2), _p(x2), _p(dW), _p(db), R, cin, cout, _p(ws), nb, _stream(),
+              nbytes=4 * R * (cin + cout) + 4 * cin * cout, tag=f"R{R}x{cout}x{cin}")
     return dW, db
 
 
@@ -202,7 +238,7 @@ class _PReLU(torch.autograd.Function):
             raise RuntimeError("gcl_b200: PReLU with one shared slope only (reference: nn.PReLU())")
         y = torch.empty_like(xc)
         with torch.cuda.device(xc.device):
-            _call("gcl_prelu_fwd_f32", _p(xc), _p(sc), _p(y), xc.numel(), _stream())
+            _call("gcl_prelu_fwd_f32", _p(xc), _p(sc), _p(y), xc.numel(), _stream(), nbytes=8 * xc.numel())
         ctx.save_for_backward(xc, sc)
         return y
 
@@ -233,7 +269,7 @@ class _LayerNorm(torch.autograd.Function):
         rstd = torch.empty(R, dtype=torch.float32, device=xc.device)
         with torch.cuda.device(xc.device):
             _call("gcl_layernorm_fwd_f32", _p(x2), _p(g), _p(b), _p(y), _p(mean), _p(rstd), R, C, float(eps),
-                  _stream())
+                  _stream(), nbytes=8 * R * C + 8 * R, tag=f"R{R}xC{C}")
         ctx.affine = gamma is not None
         ctx.save_for_backward(x2, g, mean, rstd)
         return y.view_as(xc)
@@ -251,7 +287,7 @@ class _LayerNorm(torch.autograd.Function):
         ws = _ws(nb, x2.device)
         with torch.cuda.device(x2.device):
             _call("gcl_layernorm_bwd_f32", _p(d2), _p(x2), _p(g), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db), R, C,
-                  _p(ws), nb, _stream())
+                  _p(ws), nb, _stream(), nbytes=12 * R * C + 8 * R, tag=f"R{R}xC{C}")
         return dx.view_as(dy), dg, db, None
 
 
@@ -280,10 +316,12 @@ class _GAT(torch.autograd.Function):
         alpha = torch.empty((B, max(nnz, 1), H), dtype=torch.float32, device=dev)
         alpha_pyg = torch.empty((B, max(nnz, 1), H), dtype=torch.float32, device=dev) if want_alpha else None
         with torch.cuda.device(dev):
-            _call("gcl_gat_scores_f32", _p(z3), _p(a_s), _p(a_d), _p(asrc), _p(adst), B * N, H, C, _stream())
+            _call("gcl_gat_scores_f32", _p(z3), _p(a_s), _p(a_d), _p(asrc), _p(adst), B * N, H, C, _stream(),
+                  nbytes=4 * B * N * (H * C + 2 * H), tag=f"R{B * N}xH{H}xC{C}")
             _call("gcl_gat_fwd_f32", _p(graph.rowptr), _p(graph.col), _p(graph.perm), _p(z3), _p(asrc), _p(adst),
                   _p(bias_c), _p(out), _p(alpha), _p(alpha_pyg), B, N, nnz, H, C, int(bool(concat)), float(slope),
-                  _stream())
+                  _stream(), nbytes=4 * B * (N * (H * C + cout + 2 * H) + nnz * H * (2 if want_alpha else 1)) + 4 * nnz
+                  + 4 * (N + 1), tag=f"N{N}xH{H}xC{C}xB{B}")
         ctx.graph, ctx.H, ctx.C, ctx.concat, ctx.slope = graph, H, C, bool(concat), float(slope)
         ctx.squeeze, ctx.has_bias = squeeze, bias is not None
         ctx.save_for_backward(z3, asrc, adst, alpha, a_s, a_d)
@@ -315,9 +353,11 @@ class _GAT(torch.autograd.Function):
         with torch.cuda.device(dev):
             _call("gcl_gat_bwd_f32", _p(g.rowptr), _p(g.col), _p(g.rowptr_t), _p(g.col_t), _p(g.t2r), _p(z3),
                   _p(asrc), _p(adst), _p(alpha), _p(a_s), _p(a_d), _p(d3), _p(gbuf), _p(da_s), _p(da_d), _p(dz),
-                  B, N, g.nnz, H, C, int(ctx.concat), ctx.slope, _stream())
+                  B, N, g.nnz, H, C, int(ctx.concat), ctx.slope, _stream(),
+                  nbytes=4 * B * (N * (2 * H * C + d3.shape[-1] + 4 * H) + 3 * g.nnz * H) + 16 * g.nnz,
+                  tag=f"N{N}xH{H}xC{C}xB{B}")
             _call("gcl_gat_datt_f32", _p(z3), _p(da_s), _p(da_d), _p(datt_s), _p(datt_d), B * N, H, C, _p(ws), nb,
-                  _stream())
+                  _stream(), nbytes=4 * B * N * (H * C + 2 * H), tag=f"R{B * N}xH{H}xC{C}")
         dbias = colsum_raw(d3.view(-1, d3.shape[-1])) if ctx.has_bias else None
         if ctx.squeeze:
             dz = dz.squeeze(0)

@@ -1,0 +1,196 @@
+"""One training step of the forecast model, data-parallel over the GPUs of a box.
+
+Mirrors the loop body of /root/reference/src/train.py:160-235 (AR rollout with BPTT, residual
+prediction, latitude-weighted MSE, Adam) for B samples per GPU:
+
+  * residual add + weighted MSE + its gradient are one kernel (gcl_wmse_f32);
+  * all parameters live in ONE flat fp32 buffer (views handed to the modules), so the gradient
+    all-reduce is a single NCCL call over NVLink and Adam a single kernel (gcl_adam_f32);
+  * samples shard over ranks (rank r takes its own B samples); graphs and weights are replicated.
+    The reference has no multi-GPU code at all; effective batch = world x B.
+
+Static / forcing channel carry-forward (train.py:218-226) is not used by the BASELINE configs and is
+not implemented.
+"""
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+
+
+def lat_weights(nlat: int, nlon: int, device) -> torch.Tensor:
+    """cos(lat)/mean per grid node, [G] (train.py:53-72: expanded [lon, lat] then flattened)."""
+    w = torch.cos(torch.deg2rad(torch.linspace(-90, 90, nlat)))
+    w = w / w.mean()
+    return w.view(1, -1).expand(nlon, nlat).reshape(-1).contiguous().to(device)
+
+
+class _ResidualWMSE(torch.autograd.Function):
+    """(delta, x_last, y) -> (scale * weighted MSE, out = x_last + delta); gradient computed in forward."""
+
+    @staticmethod
+    def forward(ctx, delta, x_last, y, lat_w, inv_wsum, scale, want_state):
+        lib = _cabi.load()
+        d = delta.contiguous()
+        B, G, C = d.shape
+        for t in (x_last, y):
+            if t.stride(2) != 1 or t.stride(0) != G * t.stride(1):
+                raise RuntimeError("gcl_b200: x_last / y must be [B,G,C] views with unit channel stride")
+        out = torch.empty_like(d) if want_state else None
+        grad = torch.empty_like(d)
+        loss = torch.empty(1, dtype=torch.float32, device=d.device)
+        nb = lib.gcl_wmse_workspace_bytes(B, G, C)
+        ws = torch.empty(nb, dtype=torch.uint8, device=d.device)
+        with torch.cuda.device(d.device):
+            _cabi.check(lib.gcl_wmse_f32(d.data_ptr(), x_last.data_ptr(), x_last.stride(1), y.data_ptr(), y.stride(1),
+                                         lat_w.data_ptr() if lat_w is not None else None, float(inv_wsum),
+                                         out.data_ptr() if out is not None else None, grad.data_ptr(),
+                                         loss.data_ptr(), 0, float(scale), B, G, C, ws.data_ptr(), nb,
+                                         torch.cuda.current_stream().cuda_stream), "gcl_wmse_f32")
+        ctx.save_for_backward(grad)
+        ctx.x_needs = ctx.needs_input_grad[1]
+        if want_state:
+            return loss.squeeze(0), out
+        return loss.squeeze(0), None
+
+    @staticmethod
+    def backward(ctx, dloss, dout=None):
+        (g,) = ctx.saved_tensors
+        d = g * dloss
+        if dout is not None:
+            d = d + dout
+        return d, (d if ctx.x_needs else None), None, None, None, None, None
+
+
+class Trainer:
+    """Owns the flat parameter / gradient / Adam-state buffers of `model` and runs training steps."""
+
+    def __init__(self, model: torch.nn.Module, nlat: int, nlon: int, lr: float = 1e-3, ar_steps: int = 1,
+                 use_latitude_weighting: bool = True, use_residual: bool = True, betas=(0.9, 0.999),
+                 eps: float = 1e-8, process_group=None):
+        self.model = model
+        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        self.ar_steps, self.use_residual = int(ar_steps), use_residual
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        params, seen = [], set()
+        for p in model.parameters():
+            if id(p) not in seen:
+                seen.add(id(p))
+                params.append(p)
+        self.params = params
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat_param[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat_param[off:off + k].view_as(p)
+            p.grad = self.flat_grad[off:off + k].view_as(p)
+            off += k
+        self.num_params = n
+        self.lat_w = lat_weights(nlat, nlon, dev) if use_latitude_weighting else None
+        self.G = nlat * nlon
+        self._wsum = float(self.lat_w.sum()) if self.lat_w is not None else float(self.G)  # one-time sync
+        if self.world > 1:   # identical replicas: take rank 0's initial weights
+            dist.broadcast(self.flat_param, src=0, group=self.pg)
+
+    # -- pieces, so a caller (bench.py) can graph-capture forward+backward and keep the collective eager
+    def loss(self, X: torch.Tensor, y: torch.Tensor, attention_threshold: float = 0.0, **kwargs) -> torch.Tensor:
+        """Mean over AR steps of the weighted MSE (train.py:173-231).  X [B,G,obs*C], y [B,G,steps*C]."""
+        model = self.model
+        B, G, _ = X.shape
+        obs = model.obs_window
+        C = X.shape[-1] // obs
+        tsteps = y.shape[-1] // C
+        steps = min(self.ar_steps, tsteps)
+        wsum = self._wsum * B * C          # sum of all loss weights (train.py:101)
+        ys = y.view(B, G, tsteps, C)
+        state = X.view(B, G, obs, C)
+        total = None
+        for s in range(steps):
+            delta = model(X=state.reshape(B, G, obs * C), attention_threshold=attention_threshold, **kwargs)
+            if delta.dim() == 2:
+                delta = delta.unsqueeze(0)
+            if not self.use_residual:
+                raise NotImplementedError("gcl_b200.Trainer: use_residual=False is not used by the BASELINE configs")
+            last = s == steps - 1
+            l, out = _ResidualWMSE.apply(delta, state[:, :, -1, :], ys[:, :, s, :], self.lat_w, 1.0 / wsum,
+                                         1.0 / steps, not last)
+            total = l if total is None else total + l
+            if not last:
+                state = torch.cat([state[:, :, 1:, :], out.unsqueeze(2)], dim=2)
+        return total
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def reduce_gradients(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def optimizer_step(self):
+        lib = _cabi.load()
+        with torch.cuda.device(self.flat_param.device):
+            _cabi.check(lib.gcl_adam_f32(self.flat_param.data_ptr(), self.flat_grad.data_ptr(),
+                                         self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.num_params,
+                                         self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world,
+                                         self.step_count.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                        "gcl_adam_f32")
+
+    # -- CUDA-graph fast path: forward + backward of a fixed batch shape captured once, replayed per step
+    def capture(self, batch: int, tf: int, yf: int, attention_threshold: float = 0.0, warmup: int = 2):
+        """Allocate static input buffers [batch, G, tf] / [batch, G, yf] and capture zero_grad + forward +
+        backward into one CUDA graph (every gcl_* entry point is enqueue-only).  The gradient all-reduce
+        and Adam stay outside the graph (one NCCL call + two tiny kernels)."""
+        dev = self.flat_param.device
+        self.static_x = torch.zeros(batch, self.G, tf, dtype=torch.float32, device=dev)
+        self.static_y = torch.zeros(batch, self.G, yf, dtype=torch.float32, device=dev)
+        self.static_x.normal_()
+        self.static_y.normal_()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):      # builds the CSR caches (they sync) before capture
+                self.zero_grad()
+                self.loss(self.static_x, self.static_y, attention_threshold).backward()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        lib = _cabi.load()
+        before = lib.gcl_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.zero_grad()
+            self.static_loss = self.loss(self.static_x, self.static_y, attention_threshold)
+            self.static_loss.backward()
+        self.launches_in_graph = int(lib.gcl_launch_count() - before)
+        return self
+
+    def step_captured(self) -> torch.Tensor:
+        """One training step on whatever is in static_x / static_y (device resident)."""
+        self.graph.replay()
+        self.reduce_gradients()
+        self.optimizer_step()
+        return self.static_loss
+
+    def step_from_host(self, X_pinned: torch.Tensor, y_pinned: torch.Tensor) -> float:
+        """End-to-end step from pinned host buffers: H2D copies, captured step, loss read back."""
+        self.static_x.copy_(X_pinned, non_blocking=True)
+        self.static_y.copy_(y_pinned, non_blocking=True)
+        return float(self.step_captured().item())
+
+    def step(self, X: torch.Tensor, y: torch.Tensor, attention_threshold: float = 0.0, **kwargs) -> torch.Tensor:
+        """forward + backward + gradient all-reduce + Adam; returns the (local) loss as a 0-d tensor."""
+        self.zero_grad()
+        loss = self.loss(X, y, attention_threshold, **kwargs)
+        loss.backward()
+        self.reduce_gradients()
+        self.optimizer_step()
+        return loss.detach()

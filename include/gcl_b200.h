@@ -40,6 +40,8 @@ extern "C" {
 int gcl_version(void);
 /* Thread-local text of the last error returned on this host thread ("" if none). */
 const char* gcl_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+long long gcl_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  graph -> CSR.  Replaces, per call of GCNConv/GATConv/SimpleConv.forward, PyG's
@@ -182,6 +184,35 @@ size_t gcl_edge_prune_workspace_bytes(int64_t nnz);
 int gcl_edge_prune(const int64_t* ei_pyg, const float* alpha_pyg, int64_t nnz, int64_t ei_stride,
                    float threshold, int64_t* ei_kept, int64_t kept_stride, int32_t* count_out,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a10/a12  graph construction searches (one-time, fp64, fixed operation order, no FP contraction).
+ *
+ * Grid -> mesh radius query (create_graphs.py:126-153 -> grid_mesh_connectivity.py:53-104, scipy
+ * cKDTree.query_ball_point): mesh vertex m is a hit of grid point g when
+ * ((dx^2 + dy^2) + dz^2) <= radius^2 in fp64.  Two calls: _count fills offsets[G+1] (exclusive scan of
+ * the per-point hit counts; offsets[G] = E), the caller allocates [2, E] and _fill writes
+ * row 0 = g, row 1 = mesh_index_offset + m, senders ascending, receivers ascending within a sender
+ * (the reference's receiver order inside a sender is cKDTree traversal order: compare as sets).
+ * grid_xyz fp64 [G,3], mesh_xyz fp32 [M,3].
+ */
+size_t gcl_radius_query_workspace_bytes(int64_t n_grid);
+int gcl_radius_query_count(const double* grid_xyz, const float* mesh_xyz, int64_t n_grid,
+                           int64_t n_mesh, double radius, int32_t* offsets, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int gcl_radius_query_fill(const double* grid_xyz, const float* mesh_xyz, int64_t n_grid,
+                          int64_t n_mesh, double radius, const int32_t* offsets,
+                          int64_t* edge_index_out, int64_t num_edges, int64_t mesh_index_offset,
+                          void* stream);
+/* Mesh -> grid containing triangle (create_graphs.py:271-289 -> grid_mesh_connectivity.py:139-184,
+ * trimesh.proximity.closest_point): face_out[g] = id of the mesh triangle closest to grid point g
+ * (Ericson closest point, tol.zero 1e-13; best two by squared distance, ties to the lower face id;
+ * normal-alignment rule when both exceed tol.merge 1e-8 and differ by less).  Faces whose first
+ * vertex is farther than prefilter_radius from the point are skipped (pass >= 3 max edge lengths).
+ */
+int gcl_closest_face(const double* grid_xyz, const float* mesh_xyz, const int32_t* faces,
+                     int64_t n_grid, int64_t n_mesh, int64_t n_faces, double prefilter_radius,
+                     int32_t* face_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a9/a14  glue of one forecast / training step (models.py:776-806, train.py:85-102,203-213; Adam).

@@ -153,7 +153,7 @@ class WeatherPrediction(nn.Module):
 
     def _one(self, X, attention_threshold, **kwargs):
         X = torch.cat((X, self.init_grid_features), dim=-1)
-        mesh = torch.cat((torch.zeros(self.M, self.total_feature_size), self.init_mesh_features), dim=-1)
+        mesh = torch.cat((torch.zeros(self.M, self.total_feature_size, device=X.device), self.init_mesh_features), dim=-1)
         enc = self.encoder(X=torch.cat((X, mesh), dim=0), edge_index=self.encoding_graph)
         grid_lat, mesh_lat = enc[: self.G], enc[self.G:]
         if self.using_sparse_gat:
