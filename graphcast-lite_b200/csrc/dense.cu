@@ -351,6 +351,16 @@ ColsumPlan colsum_plan(int64_t R) {
 }  // namespace
 }  // namespace gcl
 
+namespace gcl {
+int umma_linear(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
+                const float* slope, float* z_out, cudaStream_t s);   // umma_gemm.cu
+int umma_dw_splits(int64_t R, int64_t M, int64_t N);
+int umma_dw(const float* A, const float* B, float* part, float* part_colsum, int64_t R, int64_t M, int64_t N,
+            cudaStream_t s);
+static int g_dense_mode = GCL_DENSE_AUTO;
+constexpr int64_t kUmmaMinRows = 2048;   // below this the FFMA kernel's many small CTAs win
+}  // namespace gcl
+
 using namespace gcl;
 
 extern "C" int gcl_linear_fwd_f32(const float* x, const float* W, const float* bias, float* y, int64_t rows,
@@ -361,6 +371,11 @@ extern "C" int gcl_linear_fwd_f32(const float* x, const float* W, const float* b
                 "gcl_linear_fwd_f32: bad sizes rows=%lld c_in=%lld c_out=%lld", (long long)rows, (long long)c_in,
                 (long long)c_out);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rows == 0) return GCL_OK;
+  if (g_dense_mode != GCL_DENSE_FFMA && rows >= kUmmaMinRows) {   // tcgen05 3xTF32: W [Cout, Cin] is already N x K, K-major
+    const int rc = umma_linear(x, W, y, rows, c_out, c_in, bias, prelu_slope, z_out, s);
+    if (rc != GCL_ERR_UNSUPPORTED) return rc;
+  }
   dim3 tg((unsigned)ceil_div(c_in, 32), (unsigned)ceil_div(c_out, 32));
   transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(W, wt_scratch, (int)c_out, (int)c_in);
   GCL_CHECK_LAUNCH("gcl_linear_fwd_f32(transpose)");
@@ -368,17 +383,38 @@ extern "C" int gcl_linear_fwd_f32(const float* x, const float* W, const float* b
 }
 
 extern "C" int gcl_linear_bwd_dx_f32(const float* dy, const float* W, float* dx, int64_t rows, int64_t c_in,
-                                     int64_t c_out, void* stream) {
-  GCL_CHECK_ARG(dy && W && dx, "gcl_linear_bwd_dx_f32: null pointer argument");
+                                     int64_t c_out, float* wt_scratch, void* stream) {
+  GCL_CHECK_ARG(dy && W && dx && wt_scratch, "gcl_linear_bwd_dx_f32: null pointer argument");
   GCL_CHECK_ARG(rows >= 0 && c_in > 0 && c_out > 0 && c_in <= 65536 && c_out <= 65536,
                 "gcl_linear_bwd_dx_f32: bad sizes");
-  return gemm_nn(dy, W, dx, rows, c_in, c_out, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rows == 0) return GCL_OK;
+  if (g_dense_mode != GCL_DENSE_FFMA && rows >= kUmmaMinRows) {   // tcgen05 wants N x K, K-major: W^T [Cin, Cout]
+    dim3 tg((unsigned)ceil_div(c_in, 32), (unsigned)ceil_div(c_out, 32));
+    transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(W, wt_scratch, (int)c_out, (int)c_in);
+    GCL_CHECK_LAUNCH("gcl_linear_bwd_dx_f32(transpose)");
+    const int rc = umma_linear(dy, wt_scratch, dx, rows, c_in, c_out, nullptr, nullptr, nullptr, s);
+    if (rc != GCL_ERR_UNSUPPORTED) return rc;
+  }
+  return gemm_nn(dy, W, dx, rows, c_in, c_out, nullptr, nullptr, nullptr, s);
 }
+
+extern "C" int gcl_set_dense_mode(int mode) {
+  GCL_CHECK_ARG(mode == GCL_DENSE_AUTO || mode == GCL_DENSE_FFMA, "gcl_set_dense_mode: bad mode %d", mode);
+  g_dense_mode = mode;
+  return GCL_OK;
+}
+extern "C" int gcl_get_dense_mode(void) { return g_dense_mode; }
+namespace gcl { extern int g_umma_dbg; }
+extern "C" void gcl_debug_set_umma_mask(int m) { gcl::g_umma_dbg = m; }
 
 extern "C" size_t gcl_linear_bwd_dw_workspace_bytes(int64_t rows, int64_t c_in, int64_t c_out) {
   if (rows < 0 || c_in <= 0 || c_out <= 0) return 0;
   DwPlan pl = dw_plan(rows, c_out, c_in);
-  return (size_t)pl.nsplit * (size_t)(c_out * c_in + c_out) * sizeof(float) + 256;
+  int nsplit = pl.nsplit;
+  const int us = umma_dw_splits(rows, c_out, c_in);
+  if (us > nsplit) nsplit = us;
+  return (size_t)nsplit * (size_t)(c_out * c_in + c_out) * sizeof(float) + 256;
 }
 
 extern "C" int gcl_linear_bwd_dw_f32(const float* dy, const float* x, float* dW, float* dbias, int64_t rows,
@@ -398,8 +434,23 @@ extern "C" int gcl_linear_bwd_dw_f32(const float* dy, const float* x, float* dW,
     if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * M, s);
     return GCL_OK;
   }
-  DwPlan pl = dw_plan(rows, M, N);
   float* part = static_cast<float*>(workspace);
+  if (g_dense_mode != GCL_DENSE_FFMA && rows >= kUmmaMinRows) {   // tcgen05 3xTF32, rows split over <= 148 CTAs
+    const int us = umma_dw_splits(rows, M, N);
+    if (us > 0) {
+      float* upcs = part + (size_t)us * M * N;
+      const int rc = umma_dw(dy, x, part, dbias ? upcs : nullptr, rows, M, N, s);
+      if (rc != GCL_OK) return rc;
+      reduce_partials_kernel<<<(unsigned)ceil_div((int64_t)M * N, 256), 256, 0, s>>>(part, dW, (int64_t)M * N, us);
+      GCL_CHECK_LAUNCH("gcl_linear_bwd_dw_f32(reduce)");
+      if (dbias) {
+        reduce_partials_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, s>>>(upcs, dbias, M, us);
+        GCL_CHECK_LAUNCH("gcl_linear_bwd_dw_f32(reduce bias)");
+      }
+      return GCL_OK;
+    }
+  }
+  DwPlan pl = dw_plan(rows, M, N);
   float* pcs = part + (size_t)pl.nsplit * M * N;
   const int tm = pick_t(M), tn = pick_t(N);
   if (tm == 8) launch_tn_m<8>(tn, dy, x, part, dbias ? pcs : nullptr, rows, M, N, pl, s);

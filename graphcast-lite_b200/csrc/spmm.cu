@@ -44,11 +44,13 @@ struct Vec<1> {
 
 constexpr int kWarpsPerBlock = 8;
 
-template <int VW, int L>
+// SB samples of the same row per lane group: the row's (col, w) pairs are fetched once and every edge
+// issues SB independent 128-bit gathers (one per sample), which is what hides the L2/HBM latency.
+template <int VW, int L, int SB>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                 const float* __restrict__ w, const float* __restrict__ x, float* __restrict__ out,
-                int64_t n_rows, int C, int nchunks, int64_t x_bstride, int64_t out_bstride,
+                int64_t n_rows, int C, int nchunks, int64_t x_bstride, int64_t out_bstride, int B,
                 const float* __restrict__ bias, const float* __restrict__ prelu_slope,
                 float* __restrict__ z_out) {
   using V = Vec<VW>;
@@ -60,12 +62,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   const int64_t row = item / nchunks;
   const int chunk = (int)(item - row * nchunks);
   if (row >= n_rows) return;  // whole group leaves together (mask is per group)
+  const int b0 = blockIdx.y * SB;
+  const int nb = min(SB, B - b0);  // block-uniform
   const int off = (chunk * 32 + gl) * VW;  // first column this lane owns
   const bool live = off < C;
-  const float* xb = x + (int64_t)blockIdx.y * x_bstride + (live ? off : 0);
+  const float* xb = x + (int64_t)b0 * x_bstride + (live ? off : 0);
 
   const int32_t beg = rowptr[row], end = rowptr[row + 1];
-  typename V::T acc = V::zero();
+  typename V::T acc[SB];
+#pragma unroll
+  for (int s = 0; s < SB; ++s) acc[s] = V::zero();
   for (int32_t base = beg; base < end; base += L) {
     const int n = min(L, end - base);
     int32_t c_reg = 0;
@@ -74,22 +80,45 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
       c_reg = __ldg(col + base + gl);
       w_reg = w ? __ldg(w + base + gl) : 1.f;
     }
-#pragma unroll 4
+#pragma unroll 2
     for (int j = 0; j < n; ++j) {
       const int32_t c = __shfl_sync(mask, c_reg, j, L);
       const float wt = __shfl_sync(mask, w_reg, j, L);
-      if (live) V::fma(acc, wt, V::load(xb + (int64_t)c * C));
+      if (live) {
+        typename V::T v[SB];
+#pragma unroll
+        for (int s = 0; s < SB; ++s)
+          if (s < nb) v[s] = V::load(xb + (int64_t)s * x_bstride + (int64_t)c * C);
+#pragma unroll
+        for (int s = 0; s < SB; ++s)
+          if (s < nb) V::fma(acc[s], wt, v[s]);
+      }
     }
   }
   if (!live) return;
-  if (bias) acc = V::add(acc, V::load(bias + off));
-  const int64_t o = (int64_t)blockIdx.y * out_bstride + row * C + off;
-  if (z_out) V::store(z_out + o, acc);
-  if (prelu_slope) acc = V::prelu(acc, __ldg(prelu_slope));
-  V::store(out + o, acc);
+  typename V::T bv = V::zero();
+  if (bias) bv = V::load(bias + off);
+  const float slope = prelu_slope ? __ldg(prelu_slope) : 0.f;
+#pragma unroll
+  for (int s = 0; s < SB; ++s) {
+    if (s >= nb) break;
+    typename V::T a = V::add(acc[s], bv);
+    const int64_t o = (int64_t)(b0 + s) * out_bstride + row * C + off;
+    if (z_out) V::store(z_out + o, a);
+    if (prelu_slope) a = V::prelu(a, slope);
+    V::store(out + o, a);
+  }
 }
 
-template <int VW, int L>
+// samples per lane group: as many as keep SB feature matrices resident in L2 (126 MB) together
+inline int pick_sb(int64_t B, int64_t n_rows, int64_t C) {
+  const int64_t per_sample = n_rows * C * 4;
+  int sb = 8;
+  while (sb > 1 && (sb > B || sb * per_sample > (48ll << 20))) sb >>= 1;
+  return sb;
+}
+
+template <int VW, int L, int SB>
 int launch(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, float* out, int64_t B,
            int64_t n_rows, int64_t C, int64_t xbs, int64_t obs, const float* bias, const float* slope,
            float* z_out, cudaStream_t s) {
@@ -97,21 +126,32 @@ int launch(const int32_t* rowptr, const int32_t* col, const float* w, const floa
   const int nchunks = (int)ceil_div(units, 32);
   const int64_t items = n_rows * nchunks;
   const int64_t per_block = (int64_t)kWarpsPerBlock * (32 / L);
-  dim3 grid((unsigned)ceil_div(items, per_block), (unsigned)B);
-  spmm_kernel<VW, L><<<grid, kWarpsPerBlock * 32, 0, s>>>(rowptr, col, w, x, out, n_rows, (int)C, nchunks, xbs,
-                                                         obs, bias, slope, z_out);
+  dim3 grid((unsigned)ceil_div(items, per_block), (unsigned)ceil_div(B, SB));
+  spmm_kernel<VW, L, SB><<<grid, kWarpsPerBlock * 32, 0, s>>>(rowptr, col, w, x, out, n_rows, (int)C, nchunks,
+                                                             xbs, obs, (int)B, bias, slope, z_out);
   GCL_CHECK_LAUNCH("gcl_spmm_f32");
   return GCL_OK;
+}
+
+template <int VW, int L>
+int dispatch_sb(int sb, const int32_t* rowptr, const int32_t* col, const float* w, const float* x, float* out,
+                int64_t B, int64_t n_rows, int64_t C, int64_t xbs, int64_t obs, const float* bias,
+                const float* slope, float* z_out, cudaStream_t s) {
+  if (sb >= 8) return launch<VW, L, 8>(rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
+  if (sb >= 4) return launch<VW, L, 4>(rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
+  if (sb >= 2) return launch<VW, L, 2>(rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
+  return launch<VW, L, 1>(rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
 }
 
 template <int VW>
 int dispatch_l(int64_t units, const int32_t* rowptr, const int32_t* col, const float* w, const float* x,
                float* out, int64_t B, int64_t n_rows, int64_t C, int64_t xbs, int64_t obs, const float* bias,
                const float* slope, float* z_out, cudaStream_t s) {
-  if (units <= 4) return launch<VW, 4>(rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
-  if (units <= 8) return launch<VW, 8>(rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
-  if (units <= 16) return launch<VW, 16>(rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
-  return launch<VW, 32>(rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
+  const int sb = pick_sb(B, n_rows, C);
+  if (units <= 4) return dispatch_sb<VW, 4>(sb, rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
+  if (units <= 8) return dispatch_sb<VW, 8>(sb, rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
+  if (units <= 16) return dispatch_sb<VW, 16>(sb, rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
+  return dispatch_sb<VW, 32>(sb, rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
 }
 
 }  // namespace

@@ -22,7 +22,9 @@ _PROTOS = {
     "gcl_csr_weights": (c_int, [P, P, P, P, P, I64, I64, I32, P, P, P, P]),
     "gcl_spmm_f32": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, P, P, P, P]),
     "gcl_linear_fwd_f32": (c_int, [P, P, P, P, I64, I64, I64, P, P, P, P]),
-    "gcl_linear_bwd_dx_f32": (c_int, [P, P, P, I64, I64, I64, P]),
+    "gcl_linear_bwd_dx_f32": (c_int, [P, P, P, I64, I64, I64, P, P]),
+    "gcl_set_dense_mode": (c_int, [I32]),
+    "gcl_get_dense_mode": (c_int, []),
     "gcl_linear_bwd_dw_workspace_bytes": (SZ, [I64, I64, I64]),
     "gcl_linear_bwd_dw_f32": (c_int, [P, P, P, P, I64, I64, I64, P, SZ, P]),
     "gcl_colsum_workspace_bytes": (SZ, [I64, I64]),

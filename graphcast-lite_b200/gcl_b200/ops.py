@@ -130,8 +130,9 @@ def linear_bwd_dx_raw(dy2, W):
     R, cout = dy2.shape
     cin = W.shape[1]
     dx = torch.empty((R, cin), dtype=torch.float32, device=dy2.device)
+    wt = torch.empty(cin * cout, dtype=torch.float32, device=dy2.device)
     with torch.cuda.device(dy2.device):
-        _call("gcl_linear_bwd_dx_f32", _p(dy2), _p(W), _p(dx), R, cin, cout, _stream(),
+        _call("gcl_linear_bwd_dx_f32", _p(dy2), _p(W), _p(dx), R, cin, cout, _p(wt), _stream(),
               nbytes=4 * R * (cin + cout) + 4 * cin * cout, tag=f"R{R}x{cout}->{cin}")
     return dx
 

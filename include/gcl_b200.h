@@ -112,9 +112,17 @@ int gcl_spmm_f32(const int32_t* rowptr, const int32_t* col, const float* w, cons
 int gcl_linear_fwd_f32(const float* x, const float* W, const float* bias, float* y, int64_t rows,
                        int64_t c_in, int64_t c_out, const float* prelu_slope, float* z_out,
                        float* wt_scratch, void* stream);
-/* dx[R, Cin] = dy[R, Cout] W */
+/* dx[R, Cin] = dy[R, Cout] W.  wt_scratch: Cin*Cout floats (holds W^T for the tensor-core path). */
 int gcl_linear_bwd_dx_f32(const float* dy, const float* W, float* dx, int64_t rows, int64_t c_in,
-                          int64_t c_out, void* stream);
+                          int64_t c_out, float* wt_scratch, void* stream);
+/* Which engine runs the dense transforms:
+ *   GCL_DENSE_AUTO  tcgen05 tensor cores in 3xTF32 (hi/lo split, fp32 accumulate in TMEM; fp32-level
+ *                   accuracy) when the shape fits (rows >= 2048, Cout <= 256), else FFMA   [default]
+ *   GCL_DENSE_FFMA  CUDA-core fp32 FFMA kernels only (A/B comparison for the ncu evidence). */
+#define GCL_DENSE_AUTO 0
+#define GCL_DENSE_FFMA 1
+int gcl_set_dense_mode(int mode);
+int gcl_get_dense_mode(void);
 /* dW[Cout, Cin] = dy^T x ; dbias[Cout] = column sums of dy (nullable).  Deterministic split over rows. */
 size_t gcl_linear_bwd_dw_workspace_bytes(int64_t rows, int64_t c_in, int64_t c_out);
 int gcl_linear_bwd_dw_f32(const float* dy, const float* x, float* dW, float* dbias, int64_t rows,
