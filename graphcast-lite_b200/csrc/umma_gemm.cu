@@ -82,14 +82,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// hi = x rounded to tf32 (10-bit mantissa); lo = tf32 of the exact remainder
+__device__ __forceinline__ bool al16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// one contiguous, 16 B aligned chunk smem -> global through the bulk-copy (TMA) engine
+__device__ __forceinline__ void bulk_store(float* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// hi = x with the mantissa cut to tf32's 10 bits (one LOP), lo = x - hi exactly (one FADD); the tensor
+// core ignores lo's low 13 bits, so hi + lo carries >= 20 mantissa bits of x (|err| < 2^-20 |x|).  The
+// cvt.rna.tf32 route costs ~5x the instructions and the loaders are issue-bound, not precision-bound.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  const float rem = x - hi;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
-  lo = __uint_as_float(l);
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
 }
 __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float4 v) {
   float4 h, l;
@@ -129,15 +137,21 @@ __device__ __forceinline__ uint32_t sw32_off(int r, int c) {
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads, 1)
     umma_linear_kernel(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ C, int64_t M,
-                       int N, int K, int n_pad, int nkb, int nst, int tmem_cols, const float* __restrict__ bias,
-                       const float* __restrict__ prelu_slope, float* __restrict__ z_out, int dbg) {
+                       int N, int K, int n_pad, int nkb, int nst, int tmem_cols, int cw, int stage_z,
+                       const float* __restrict__ bias, const float* __restrict__ prelu_slope,
+                       float* __restrict__ z_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_block = n_pad * 128;                       // one K-block of W (hi or lo)
   uint8_t* b_hi = smem;
   uint8_t* b_lo = b_hi + (size_t)nkb * b_block;
   uint8_t* a_st = b_lo + (size_t)nkb * b_block;
-  uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(a_st + (size_t)nst * 2 * kPartBytes);
+  float* bias_s = reinterpret_cast<float*>(a_st + (size_t)nst * 2 * kPartBytes);       // n_pad floats
+  const int pitch = cw * 4 + 16;                         // staging row pitch: +16 B keeps st.shared.v4 conflict-free
+  uint8_t* c_stage = reinterpret_cast<uint8_t*>(bias_s + n_pad);                        // [128][pitch]
+  uint8_t* z_stage = c_stage + (size_t)(cw ? kTileM * pitch : 0);                      // [128][pitch] if stage_z
+  uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(
+      (reinterpret_cast<uintptr_t>(z_stage + (size_t)(stage_z ? kTileM * pitch : 0)) + 15) & ~uintptr_t(15));
   const uint32_t bars = smem_u32(bar_ptr);
   // barrier indices: full[s] = s, empty[s] = nst + s, tmem_full[a] = 2 nst + a, tmem_empty[a] = 2 nst + 2 + a
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + 2 * nst + 4);
@@ -176,6 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     split_store(b_hi + (size_t)kb * b_block, b_lo + (size_t)kb * b_block, sw_off(n, c), v);
   }
+  for (int n = tid; n < n_pad; n += kThreads) bias_s[n] = (bias && n < N) ? __ldg(bias + n) : 0.f;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -198,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int64_t row = tile * kTileM + r;
         const int k = kb * kKB + c * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < M && !(dbg & 2)) {
+        if (row < M) {
           const float* src = A + row * K + k;
           if (VEC) {
             if (k < K) v = __ldg(reinterpret_cast<const float4*>(src));
@@ -218,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     (void)nitems;
     // kDepth register buffers form a ring: a buffer is refilled right after it has been staged, so
     // kDepth items (kDepth x 16 KB per SM) are always in flight -- that, not the MMA, sets the pace.
-    constexpr int kDepth = 4;
+    constexpr int kDepth = 5;
     float4 buf[kDepth][4];
     (void)cur;
     (void)nxt;
@@ -265,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t bh = smem_u32(b_hi + (size_t)kb * b_block);
           const uint32_t bl = smem_u32(b_lo + (size_t)kb * b_block);
           const int ksteps = min(4, (K - kb * kKB + 7) / 8);
-          for (int ks = 0; ks < ksteps && !(dbg & 4); ++ks) {
+          for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t da_hi = make_desc(a_hi + ks * 32, 16, 1024), da_lo = make_desc(a_lo + ks * 32, 16, 1024);
             const uint64_t db_hi = make_desc(bh + ks * 32, 16, 1024), db_lo = make_desc(bl + ks * 32, 16, 1024);
             umma_tf32(d_tmem, da_lo, db_hi, idesc, (kb | ks) ? 1u : 0u);   // small terms first
@@ -279,44 +294,73 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> (+bias, PReLU) -> global =====================
+    // Every thread owns one output row.  With cw > 0 the row segment is staged in this thread's own smem
+    // row and leaves as ONE asynchronous bulk copy (cp.async.bulk, 16 B aligned): the direct alternative,
+    // 32 lanes storing 16 B each to 32 different rows, costs 32 LSU sector transactions per instruction
+    // and was the single largest term of the kernel time.
     const float slope = prelu_slope ? __ldg(prelu_slope) : 0.f;
+    const int my = warp * 32 + lane;
+    uint8_t* crow_s = c_stage + (size_t)my * pitch;
+    uint8_t* zrow_s = z_stage + (size_t)my * pitch;
     int64_t t_local = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_local) {
       const int acc = (int)(t_local & 1);
       mbar_wait(bars + 8 * (2 * nst + acc), (uint32_t)((t_local >> 1) & 1));
       tc_fence_after();
-      const int64_t row = tile * kTileM + warp * 32 + lane;
+      const int64_t row = tile * kTileM + my;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * n_pad);
-      for (int c0 = 0; c0 < n_pad; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        if (row < M && !(dbg & 1)) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = c0 + j;
-            if (n < N) {
-              float x = v[j];
-              if (bias) x += __ldg(bias + n);
-              v[j] = x;
-            }
-          }
-          float* crow = C + row * N + c0;
-          float* zrow = z_out ? z_out + row * N + c0 : nullptr;
-          if ((N & 3) == 0 && c0 + 16 <= N) {
+      if (cw > 0) {
+        for (int p = 0; p < N; p += cw) {
+          bulk_wait_read();                                  // my previous copies no longer read my smem rows
+          for (int c0 = p; c0 < p + cw; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + c0, v);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-              if (zrow) *reinterpret_cast<float4*>(zrow + 4 * q) = o;
-              if (prelu_slope)
-                o = make_float4(prelu_f(o.x, slope), prelu_f(o.y, slope), prelu_f(o.z, slope), prelu_f(o.w, slope));
-              *reinterpret_cast<float4*>(crow + 4 * q) = o;
+              if (c0 + 4 * q < p + cw) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * q);
+                float4 o = make_float4(v[4 * q] + b4.x, v[4 * q + 1] + b4.y, v[4 * q + 2] + b4.z, v[4 * q + 3] + b4.w);
+                if (z_out) {
+                  if (stage_z) *reinterpret_cast<float4*>(zrow_s + (c0 - p + 4 * q) * 4) = o;
+                  else if (row < M) *reinterpret_cast<float4*>(z_out + row * N + c0 + 4 * q) = o;
+                }
+                if (prelu_slope)
+                  o = make_float4(prelu_f(o.x, slope), prelu_f(o.y, slope), prelu_f(o.z, slope), prelu_f(o.w, slope));
+                *reinterpret_cast<float4*>(crow_s + (c0 - p + 4 * q) * 4) = o;
+              }
             }
-          } else {
+          }
+          fence_proxy_async();
+          if (row < M) {
+            bulk_store(C + row * N + p, smem_u32(crow_s), (uint32_t)cw * 4);
+            if (z_out && stage_z) bulk_store(z_out + row * N + p, smem_u32(zrow_s), (uint32_t)cw * 4);
+          }
+          bulk_commit();
+        }
+      } else {
+        const bool vec_ok = (N & 3) == 0 && al16_dev(C) && (!z_out || al16_dev(z_out));
+        for (int c0 = 0; c0 < n_pad; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          if (row < M) {
+            if (vec_ok && c0 + 16 <= N) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (c0 + j < N) {
-                if (zrow) zrow[j] = v[j];
-                crow[j] = prelu_slope ? prelu_f(v[j], slope) : v[j];
+              for (int q = 0; q < 4; ++q) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * q);
+                float4 o = make_float4(v[4 * q] + b4.x, v[4 * q + 1] + b4.y, v[4 * q + 2] + b4.z, v[4 * q + 3] + b4.w);
+                if (z_out) *reinterpret_cast<float4*>(z_out + row * N + c0 + 4 * q) = o;
+                if (prelu_slope)
+                  o = make_float4(prelu_f(o.x, slope), prelu_f(o.y, slope), prelu_f(o.z, slope), prelu_f(o.w, slope));
+                *reinterpret_cast<float4*>(C + row * N + c0 + 4 * q) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (c0 + j < N) {
+                  const float x = v[j] + bias_s[c0 + j];
+                  if (z_out) z_out[row * N + c0 + j] = x;
+                  C[row * N + c0 + j] = prelu_slope ? prelu_f(x, slope) : x;
+                }
               }
             }
           }
@@ -325,6 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_before();
       mbar_arrive(bars + 8 * (2 * nst + 2 + acc));
     }
+    bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -340,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 // exactly how the row-major tiles land in smem: per 32-column block a [32 rows x 128 B] slab in the
 // SWIZZLE_128B_BASE32B layout (LBO = 4096 B between column blocks, SBO = 512 B between 4-row atoms).  B gets one extra column
 // of ones at n = N so that column N of the accumulator is the column sum of A (the bias gradient).
-template <bool VEC>
+template <bool VEC, int NBB>
 __global__ void __launch_bounds__(kThreads, 1)
     umma_dw_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ part,
                    float* __restrict__ part_colsum, int64_t R, int M, int N, int n_pad, int nbb, int nst,
@@ -375,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp > kEpiWarps) {
     const int lt = tid - (kEpiWarps + 1) * 32;
     constexpr int kDepth = 2;
-    constexpr int kMaxB = 8;                               // float4 of B per thread per item (nbb <= 8)
+    constexpr int kMaxB = NBB;                             // float4 of B per thread per item (nbb <= NBB)
     float4 abuf[kDepth][4], bbuf[kDepth][kMaxB];
     const int nch = nbb * 8;                               // 16-byte chunks per B row
     auto fetch = [&](int64_t kb, float4 (&da)[4], float4 (&db)[kMaxB]) {
@@ -513,24 +558,43 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 struct LinPlan {
-  int n_pad, nkb, nst, tmem_cols;
+  int n_pad, nkb, nst, tmem_cols, cw, stage_z;
   size_t smem;
   bool ok;
 };
 
-LinPlan plan_linear(int64_t N, int64_t K) {
+LinPlan plan_linear(int64_t N, int64_t K, bool has_z, bool c_aligned) {
   LinPlan p{};
   p.n_pad = (int)((N + 15) / 16 * 16);
   p.nkb = (int)((K + kKB - 1) / kKB);
-  const size_t b_bytes = (size_t)2 * p.nkb * p.n_pad * 128;
-  const size_t fixed = 1024 /*align slack*/ + 256 /*barriers*/;
   p.ok = N >= 1 && p.n_pad <= 256 && K >= 1;
   if (!p.ok) return p;
-  const long room = (long)kMaxSmem - (long)b_bytes - (long)fixed;
-  p.nst = (int)(room / (2 * kPartBytes));
-  if (p.nst > 6) p.nst = 6;
-  p.ok = p.nst >= 2;
-  p.smem = b_bytes + (size_t)p.nst * 2 * kPartBytes + fixed;
+  const long b_bytes = 2L * p.nkb * p.n_pad * 128;
+  const long fixed = 1024 /*align slack*/ + 256 /*barriers*/ + 16 + 4L * p.n_pad /*bias*/;
+  int cands[8], nc = 0;
+  if (N % 4 == 0 && c_aligned) {
+    cands[nc++] = (int)N;   // one bulk copy per row and tile; partial-row passes would serialise on wait_group.read
+  }
+  cands[nc++] = 0;   // direct stores
+  int best_nst = 0;
+  for (int want = 3; want >= 2 && best_nst == 0; --want) {
+    for (int i = 0; i < nc && best_nst == 0; ++i) {
+      for (int sz = (has_z && cands[i] > 0) ? 1 : 0; sz >= 0 && best_nst == 0; --sz) {
+        const long staging = cands[i] ? (1L + sz) * kTileM * (cands[i] * 4 + 16) : 0;
+        const long room = (long)kMaxSmem - b_bytes - fixed - staging;
+        int nst = (int)(room / (2 * kPartBytes));
+        if (nst > 6) nst = 6;
+        if (nst >= want) {
+          best_nst = nst;
+          p.cw = cands[i];
+          p.stage_z = sz;
+          p.smem = (size_t)(b_bytes + fixed + staging + (long)nst * 2 * kPartBytes);
+        }
+      }
+    }
+  }
+  p.nst = best_nst;
+  p.ok = best_nst >= 2;
   int cols = 32;
   while (cols < 2 * p.n_pad) cols <<= 1;
   p.tmem_cols = cols;
@@ -541,13 +605,12 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 }  // namespace
 
-int g_umma_dbg = 0;   // development only: bit0 skip epilogue stores, bit1 skip A loads, bit2 skip MMAs
 
 // Returns GCL_OK when launched, GCL_ERR_UNSUPPORTED when the shape does not fit (caller falls back to
 // the FFMA kernel), or an error.
 int umma_linear(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
                 const float* slope, float* z_out, cudaStream_t s) {
-  LinPlan p = plan_linear(N, K);
+  LinPlan p = plan_linear(N, K, z_out != nullptr, al16(C) && (!z_out || al16(z_out)));
   if (!p.ok || M <= 0) return GCL_ERR_UNSUPPORTED;
   const bool vec = (K % 4 == 0) && al16(A) && al16(W_nk);
   const int64_t ntiles = (M + kTileM - 1) / kTileM;
@@ -557,12 +620,12 @@ int umma_linear(const float* A, const float* W_nk, float* C, int64_t M, int64_t 
     e = cudaFuncSetAttribute(umma_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return fail_cuda(e, "umma_linear(smem attr)");
     umma_linear_kernel<true><<<grid, kThreads, p.smem, s>>>(A, W_nk, C, M, (int)N, (int)K, p.n_pad, p.nkb, p.nst,
-                                                            p.tmem_cols, bias, slope, z_out, g_umma_dbg);
+                                                            p.tmem_cols, p.cw, p.stage_z, bias, slope, z_out);
   } else {
     e = cudaFuncSetAttribute(umma_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return fail_cuda(e, "umma_linear(smem attr)");
     umma_linear_kernel<false><<<grid, kThreads, p.smem, s>>>(A, W_nk, C, M, (int)N, (int)K, p.n_pad, p.nkb, p.nst,
-                                                             p.tmem_cols, bias, slope, z_out, g_umma_dbg);
+                                                             p.tmem_cols, p.cw, p.stage_z, bias, slope, z_out);
   }
   GCL_CHECK_LAUNCH("umma_linear");
   return GCL_OK;
@@ -610,18 +673,18 @@ int umma_dw(const float* A, const float* B, float* part, float* part_colsum, int
   DwUmmaPlan p = plan_dw(R, M, N);
   if (!p.ok) return GCL_ERR_UNSUPPORTED;
   const bool vec = (M % 4 == 0) && (N % 4 == 0) && al16(A) && al16(B);
-  cudaError_t e;
-  if (vec) {
-    e = cudaFuncSetAttribute(umma_dw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  auto go = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return fail_cuda(e, "umma_dw(smem attr)");
-    umma_dw_kernel<true><<<p.grid, kThreads, p.smem, s>>>(A, B, part, part_colsum, R, (int)M, (int)N, p.n_pad, p.nbb,
-                                                          p.nst, p.tmem_cols, p.rows_per_cta);
-  } else {
-    e = cudaFuncSetAttribute(umma_dw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-    if (e != cudaSuccess) return fail_cuda(e, "umma_dw(smem attr)");
-    umma_dw_kernel<false><<<p.grid, kThreads, p.smem, s>>>(A, B, part, part_colsum, R, (int)M, (int)N, p.n_pad, p.nbb,
-                                                           p.nst, p.tmem_cols, p.rows_per_cta);
-  }
+    kern<<<p.grid, kThreads, p.smem, s>>>(A, B, part, part_colsum, R, (int)M, (int)N, p.n_pad, p.nbb, p.nst,
+                                          p.tmem_cols, p.rows_per_cta);
+    return GCL_OK;
+  };
+  int rc;
+  if (p.nbb <= 2) rc = vec ? go(umma_dw_kernel<true, 2>) : go(umma_dw_kernel<false, 2>);
+  else if (p.nbb <= 4) rc = vec ? go(umma_dw_kernel<true, 4>) : go(umma_dw_kernel<false, 4>);
+  else rc = vec ? go(umma_dw_kernel<true, 8>) : go(umma_dw_kernel<false, 8>);
+  if (rc != GCL_OK) return rc;
   GCL_CHECK_LAUNCH("umma_dw");
   return GCL_OK;
 }
