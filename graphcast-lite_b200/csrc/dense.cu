@@ -434,9 +434,7 @@ extern "C" int gcl_linear_bwd_dw_f32(const float* dy, const float* x, float* dW,
     return GCL_OK;
   }
   float* part = static_cast<float*>(workspace);
-  // tcgen05 3xTF32 with MN-major operands runs ~3.4x below the K-major MMA rate (measured), so it only wins
-  // over the FFMA kernel when one of the two widths exceeds 64
-  if (g_dense_mode != GCL_DENSE_FFMA && rows >= kUmmaMinRows && (M > 64 || N > 64)) {
+  if (g_dense_mode != GCL_DENSE_FFMA && rows >= kUmmaMinRows) {   // tcgen05 3xTF32, rows split over <= 148 CTAs
     const int us = umma_dw_splits(rows, M, N);
     if (us > 0) {
       float* upcs = part + (size_t)us * M * N;

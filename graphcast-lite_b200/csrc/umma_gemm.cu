@@ -12,7 +12,7 @@
 //
 // Persistent, warp-specialised CTAs (one per SM): warps 0-3 epilogue (TMEM -> registers -> global; a
 // warp may only touch TMEM lanes 32*(warp%4)..+31), warp 4 allocates TMEM and its lane 0 issues the
-// MMAs, warps 5-12 load/split/stage.  mbarrier rings: full/empty per smem stage, full/empty per TMEM
+// MMAs, warps 5-11 load/split/stage.  mbarrier rings: full/empty per smem stage, full/empty per TMEM
 // accumulator (two accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1).
 #include "common.cuh"
 
@@ -22,8 +22,10 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kKB = 32;                        // fp32 elements per 128-byte swizzle row
 constexpr int kPartBytes = kTileM * 128;       // one 128-row x 128-byte operand block (hi or lo): 16 KB
-constexpr int kEpiWarps = 4, kLoadWarps = 8;
-constexpr int kThreads = (kEpiWarps + 1 + kLoadWarps) * 32;   // 416
+// 12 warps = 3 per SM sub-partition, which lets every thread have up to 168 registers (13 warps would put
+// 4 on one sub-partition and cap everything at 128: the loaders' prefetch ring then spills).
+constexpr int kEpiWarps = 4, kLoadWarps = 7;
+constexpr int kThreads = (kEpiWarps + 1 + kLoadWarps) * 32;   // 384
 constexpr int kLoadThreads = kLoadWarps * 32;
 constexpr int kMaxSmem = 227 * 1024;
 
@@ -127,11 +129,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
 // byte offset of 16-byte chunk `c` (0..7) of row `r` inside a [rows x 128 B] swizzled block
 __device__ __forceinline__ uint32_t sw_off(int r, int c) { return (uint32_t)(r * 128 + (((c ^ (r & 7)) & 7) << 4)); }
 
-// same for the 128B_BASE32B swizzle: 16-byte chunk c of row r; its 32-byte chunk index is XORed with r % 4
-__device__ __forceinline__ uint32_t sw32_off(int r, int c) {
-  return (uint32_t)(r * 128 + ((((c >> 1) ^ (r & 3)) & 3) << 5) + ((c & 1) << 4));
-}
-
 // ------------------------------------------------------------------------------------------------
 // C[M,N] = A[M,K] W[N,K]^T  (K-major operands).  VEC: K % 4 == 0 and 16 B aligned A / W rows.
 template <bool VEC>
@@ -199,21 +196,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp > kEpiWarps) {
     // ===================== loaders: global A -> registers -> hi/lo -> swizzled smem stage =====================
-    const int lt = tid - (kEpiWarps + 1) * 32;           // 0..255
+    const int lt = tid - (kEpiWarps + 1) * 32;           // 0..223
     const int64_t nitems = ntiles * nkb;
     int64_t it_local = 0;
-    float4 cur[4], nxt[4];
-    auto fetch = [&](int64_t item, float4 (&dst)[4]) {
+    constexpr int kPer = (1024 + kLoadThreads - 1) / kLoadThreads;   // 16-byte chunks per thread per stage (5)
+    auto fetch = [&](int64_t item, float4 (&dst)[kPer]) {
       const int64_t tile = blockIdx.x + (item / nkb) * gridDim.x;
       const int kb = (int)(item % nkb);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int id = lt + i * kLoadThreads;              // 0..1023
+      for (int i = 0; i < kPer; ++i) {
+        const int id = lt + i * kLoadThreads;              // 0..1023 valid
         const int r = id >> 3, c = id & 7;
         const int64_t row = tile * kTileM + r;
         const int k = kb * kKB + c * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < M) {
+        if (id < 1024 && row < M) {
           const float* src = A + row * K + k;
           if (VEC) {
             if (k < K) v = __ldg(reinterpret_cast<const float4*>(src));
@@ -234,9 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // kDepth register buffers form a ring: a buffer is refilled right after it has been staged, so
     // kDepth items (kDepth x 16 KB per SM) are always in flight -- that, not the MMA, sets the pace.
     constexpr int kDepth = 5;
-    float4 buf[kDepth][4];
-    (void)cur;
-    (void)nxt;
+    float4 buf[kDepth][kPer];
 #pragma unroll
     for (int d = 0; d < kDepth; ++d)
       if (d < my_items) fetch(d, buf[d]);
@@ -251,9 +246,9 @@ __global__ void __launch_bounds__(kThreads, 1)
           uint8_t* hi = a_st + (size_t)st * 2 * kPartBytes;
           uint8_t* lo = hi + kPartBytes;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < kPer; ++i) {
             const int id = lt + i * kLoadThreads;
-            split_store(hi, lo, sw_off(id >> 3, id & 7), buf[d][i]);
+            if (id < 1024) split_store(hi, lo, sw_off(id >> 3, id & 7), buf[d][i]);
           }
           fence_proxy_async();
           mbar_arrive(bars + 8 * st);
@@ -381,18 +376,20 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 // ------------------------------------------------------------------------------------------------
 // P[s][m][n] = sum over the CTA's row slice of A[r][m] * B[r][n]   (dW = dY^T X, split over rows).
-// Both operands are "MN-major" for the MMA (the reduction index r is the slow one in memory), which is
-// exactly how the row-major tiles land in smem: per 32-column block a [32 rows x 128 B] slab in the
-// SWIZZLE_128B_BASE32B layout (LBO = 4096 B between column blocks, SBO = 512 B between 4-row atoms).  B gets one extra column
-// of ones at n = N so that column N of the accumulator is the column sum of A (the bias gradient).
-template <bool VEC, int NBB>
+// The reduction index r is the slow one in memory, i.e. both operands arrive "MN-major".  tcgen05 can
+// read MN-major tf32 (SWIZZLE_128B_BASE32B), but that path measured ~3.4x below the K-major MMA rate,
+// so the loaders transpose instead: a lane owns one column m and reads it for 4 consecutive rows
+// (4 warp-coalesced 128-byte loads), which is exactly one 16-byte K-chunk of smem row m in the K-major
+// SWIZZLE_128B layout -- consecutive lanes hit different swizzled chunks, so the stores are conflict-free.
+// B gets a constant row n = N of ones, so accumulator column N is the column sum of A (bias gradient).
+template <int NAU, int NBU>   // units (32 columns x 4 rows) per loader warp for A and B
 __global__ void __launch_bounds__(kThreads, 1)
     umma_dw_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ part,
-                   float* __restrict__ part_colsum, int64_t R, int M, int N, int n_pad, int nbb, int nst,
-                   int tmem_cols, int64_t rows_per_cta) {
+                   float* __restrict__ part_colsum, int64_t R, int M, int N, int n_pad, int nst, int tmem_cols,
+                   int64_t rows_per_cta) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_part = nbb * 4096;                           // hi or lo of the B stage
+  const int b_part = n_pad * 128;                          // hi or lo of the B stage: [n_pad rows x 128 B]
   const int stage_bytes = 2 * kPartBytes + 2 * b_part;     // A_hi, A_lo, B_hi, B_lo
   uint8_t* st_base = smem;
   uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(st_base + (size_t)nst * stage_bytes);
@@ -412,60 +409,88 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kEpiWarps) tmem_alloc(smem_u32(tmem_slot), (uint32_t)tmem_cols);
+  // constant parts of every stage: zero everything, then the row of ones (hi = 1, lo = 0) at n = N
+  for (int i = tid; i < nst * stage_bytes / 16; i += kThreads)
+    reinterpret_cast<float4*>(st_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (int i = tid; i < nst * 8; i += kThreads) {
+    uint8_t* b_hi = st_base + (size_t)(i >> 3) * stage_bytes + 2 * kPartBytes;
+    *reinterpret_cast<float4*>(b_hi + sw_off(N, i & 7)) = make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp > kEpiWarps) {
-    const int lt = tid - (kEpiWarps + 1) * 32;
+    const int lw = warp - (kEpiWarps + 1);                 // 0..6
+    const int na_units = 8 * ((M + 31) / 32), nb_units = 8 * ((N + 31) / 32);
     constexpr int kDepth = 2;
-    constexpr int kMaxB = NBB;                             // float4 of B per thread per item (nbb <= NBB)
-    float4 abuf[kDepth][4], bbuf[kDepth][kMaxB];
-    const int nch = nbb * 8;                               // 16-byte chunks per B row
-    auto fetch = [&](int64_t kb, float4 (&da)[4], float4 (&db)[kMaxB]) {
+    float4 abuf[kDepth][NAU], bbuf[kDepth][NBU];
+    // per-unit element offsets relative to the first row of a K-block (-1 = unit or column out of range)
+    int offa[NAU], offb[NBU];
+#pragma unroll
+    for (int i = 0; i < NAU; ++i) {
+      const int u = lw + kLoadWarps * i, m = (u >> 3) * 32 + lane;
+      offa[i] = (u < na_units && m < M) ? (u & 7) * 4 * M + m : -1;
+    }
+#pragma unroll
+    for (int i = 0; i < NBU; ++i) {
+      const int u = lw + kLoadWarps * i, n = (u >> 3) * 32 + lane;
+      offb[i] = (u < nb_units && n < N) ? (u & 7) * 4 * N + n : -1;
+    }
+    auto fetch = [&](int64_t kb, float4 (&da)[NAU], float4 (&db)[NBU]) {
       const int64_t r0 = r_beg + kb * kKB;
+      const float* pa = A + r0 * M;
+      const float* pb = B + r0 * N;
+      if (r0 + kKB <= r_end) {                              // full K-block: no row guards
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int id = lt + i * kLoadThreads;              // 0..1023 = 32 rows x 32 chunks
-        const int r = id >> 5, cm = id & 31;
-        const int64_t row = r0 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < r_end) {
-          const int m = cm * 4;
-          const float* src = A + row * M + m;
-          if (VEC) {
-            if (m < M) v = __ldg(reinterpret_cast<const float4*>(src));
-          } else {
-            if (m + 0 < M) v.x = __ldg(src + 0);
-            if (m + 1 < M) v.y = __ldg(src + 1);
-            if (m + 2 < M) v.z = __ldg(src + 2);
-            if (m + 3 < M) v.w = __ldg(src + 3);
+        for (int i = 0; i < NAU; ++i) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (offa[i] >= 0) {
+            const float* src = pa + offa[i];
+            v = make_float4(__ldg(src), __ldg(src + M), __ldg(src + 2 * M), __ldg(src + 3 * M));
           }
+          da[i] = v;
         }
-        da[i] = v;
-      }
 #pragma unroll
-      for (int i = 0; i < kMaxB; ++i) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < nbb) {
-          const int id = lt + i * kLoadThreads;            // 32 rows x nch chunks
-          const int r = id / nch, cn = id % nch;
-          const int64_t row = r0 + r;
-          if (row < r_end) {
-            const int n = cn * 4;
-            const float* src = B + row * N + n;
-            if (VEC && n + 4 <= N) {
-              v = __ldg(reinterpret_cast<const float4*>(src));
-            } else {
-              v.x = (n + 0 < N) ? __ldg(src + 0) : ((n + 0 == N) ? 1.f : 0.f);
-              v.y = (n + 1 < N) ? __ldg(src + 1) : ((n + 1 == N) ? 1.f : 0.f);
-              v.z = (n + 2 < N) ? __ldg(src + 2) : ((n + 2 == N) ? 1.f : 0.f);
-              v.w = (n + 3 < N) ? __ldg(src + 3) : ((n + 3 == N) ? 1.f : 0.f);
-            }
+        for (int i = 0; i < NBU; ++i) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (offb[i] >= 0) {
+            const float* src = pb + offb[i];
+            v = make_float4(__ldg(src), __ldg(src + N), __ldg(src + 2 * N), __ldg(src + 3 * N));
           }
+          db[i] = v;
         }
-        db[i] = v;
+      } else {                                              // last, partial K-block of the slice
+        const int left = (int)(r_end - r0);
+#pragma unroll
+        for (int i = 0; i < NAU; ++i) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (offa[i] >= 0) {
+            const int rr = ((lw + kLoadWarps * i) & 7) * 4;
+            const float* src = pa + offa[i];
+            if (rr + 0 < left) v.x = __ldg(src);
+            if (rr + 1 < left) v.y = __ldg(src + M);
+            if (rr + 2 < left) v.z = __ldg(src + 2 * M);
+            if (rr + 3 < left) v.w = __ldg(src + 3 * M);
+          }
+          da[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NBU; ++i) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (offb[i] >= 0) {
+            const int rr = ((lw + kLoadWarps * i) & 7) * 4;
+            const float* src = pb + offb[i];
+            if (rr + 0 < left) v.x = __ldg(src);
+            if (rr + 1 < left) v.y = __ldg(src + N);
+            if (rr + 2 < left) v.z = __ldg(src + 2 * N);
+            if (rr + 3 < left) v.w = __ldg(src + 3 * N);
+          }
+          db[i] = v;
+        }
       }
     };
 #pragma unroll
@@ -483,18 +508,14 @@ __global__ void __launch_bounds__(kThreads, 1)
           uint8_t* b_hi = a_lo + kPartBytes;
           uint8_t* b_lo = b_hi + b_part;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int id = lt + i * kLoadThreads;
-            const int r = id >> 5, cm = id & 31;
-            split_store(a_hi, a_lo, (uint32_t)((cm >> 3) * 4096) + sw32_off(r, cm & 7), abuf[d][i]);
+          for (int i = 0; i < NAU; ++i) {
+            const int u = lw + kLoadWarps * i;
+            if (offa[i] >= 0) split_store(a_hi, a_lo, sw_off((u >> 3) * 32 + lane, u & 7), abuf[d][i]);
           }
 #pragma unroll
-          for (int i = 0; i < kMaxB; ++i) {
-            if (i < nbb) {
-              const int id = lt + i * kLoadThreads;
-              const int r = id / nch, cn = id % nch;
-              split_store(b_hi, b_lo, (uint32_t)((cn >> 3) * 4096) + sw32_off(r, cn & 7), bbuf[d][i]);
-            }
+          for (int i = 0; i < NBU; ++i) {
+            const int u = lw + kLoadWarps * i;
+            if (offb[i] >= 0) split_store(b_hi, b_lo, sw_off((u >> 3) * 32 + lane, u & 7), bbuf[d][i]);
           }
           fence_proxy_async();
           mbar_arrive(bars + 8 * st);
@@ -504,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == kEpiWarps) {
     if (lane == 0 && nkb > 0) {
-      const uint32_t idesc = make_idesc(n_pad, 1, 1);
+      const uint32_t idesc = make_idesc(n_pad, 0, 0);
       for (int64_t kb = 0; kb < nkb; ++kb) {
         const int st = (int)(kb % nst);
         mbar_wait(bars + 8 * st, (uint32_t)((kb / nst) & 1));
@@ -514,9 +535,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t b_hi = a_lo + kPartBytes;
         const uint32_t b_lo = b_hi + b_part;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {                     // 8 rows (one swizzle atom) per MMA
-          const uint64_t da_hi = make_desc(a_hi + ks * 1024, 4096, 512, 1), da_lo = make_desc(a_lo + ks * 1024, 4096, 512, 1);
-          const uint64_t db_hi = make_desc(b_hi + ks * 1024, 4096, 512, 1), db_lo = make_desc(b_lo + ks * 1024, 4096, 512, 1);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t da_hi = make_desc(a_hi + ks * 32, 16, 1024), da_lo = make_desc(a_lo + ks * 32, 16, 1024);
+          const uint64_t db_hi = make_desc(b_hi + ks * 32, 16, 1024), db_lo = make_desc(b_lo + ks * 32, 16, 1024);
           umma_tf32(tmem_base, da_lo, db_hi, idesc, (kb | ks) ? 1u : 0u);
           umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
           umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
@@ -633,18 +654,17 @@ int umma_linear(const float* A, const float* W_nk, float* C, int64_t M, int64_t 
 
 namespace {
 struct DwUmmaPlan {
-  int n_pad, nbb, nst, tmem_cols, grid;
+  int n_pad, nst, tmem_cols, grid;
   int64_t rows_per_cta;
   size_t smem;
   bool ok;
 };
 DwUmmaPlan plan_dw(int64_t R, int64_t M, int64_t N) {
   DwUmmaPlan p{};
-  p.ok = R > 0 && M >= 1 && M <= kTileM && N >= 1 && N + 1 <= 256;
+  p.ok = R > 0 && M >= 1 && M <= kTileM && N >= 1 && N <= 128;
   if (!p.ok) return p;
   p.n_pad = (int)((N + 1 + 15) / 16 * 16);
-  p.nbb = (p.n_pad + 31) / 32;
-  const size_t stage = 2 * (size_t)kPartBytes + 2 * (size_t)p.nbb * 4096;
+  const size_t stage = 2 * (size_t)kPartBytes + 2 * (size_t)p.n_pad * 128;
   const size_t fixed = 1024 + 256;
   p.nst = (int)(((size_t)kMaxSmem - fixed) / stage);
   if (p.nst > 4) p.nst = 4;
@@ -672,18 +692,21 @@ int umma_dw(const float* A, const float* B, float* part, float* part_colsum, int
             cudaStream_t s) {
   DwUmmaPlan p = plan_dw(R, M, N);
   if (!p.ok) return GCL_ERR_UNSUPPORTED;
-  const bool vec = (M % 4 == 0) && (N % 4 == 0) && al16(A) && al16(B);
   auto go = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return fail_cuda(e, "umma_dw(smem attr)");
-    kern<<<p.grid, kThreads, p.smem, s>>>(A, B, part, part_colsum, R, (int)M, (int)N, p.n_pad, p.nbb, p.nst,
-                                          p.tmem_cols, p.rows_per_cta);
+    kern<<<p.grid, kThreads, p.smem, s>>>(A, B, part, part_colsum, R, (int)M, (int)N, p.n_pad, p.nst, p.tmem_cols,
+                                          p.rows_per_cta);
     return GCL_OK;
   };
+  // (32-column x 4-row) units per loader warp: 8 * ceil(width / 32) units over 7 warps
+  const int au = (8 * (int)((M + 31) / 32) + kLoadWarps - 1) / kLoadWarps;
+  const int bu = (8 * (int)((N + 31) / 32) + kLoadWarps - 1) / kLoadWarps;
   int rc;
-  if (p.nbb <= 2) rc = vec ? go(umma_dw_kernel<true, 2>) : go(umma_dw_kernel<false, 2>);
-  else if (p.nbb <= 4) rc = vec ? go(umma_dw_kernel<true, 4>) : go(umma_dw_kernel<false, 4>);
-  else rc = vec ? go(umma_dw_kernel<true, 8>) : go(umma_dw_kernel<false, 8>);
+  if (au <= 3 && bu <= 3) rc = go(umma_dw_kernel<3, 3>);
+  else if (au <= 3) rc = go(umma_dw_kernel<3, 5>);
+  else if (bu <= 3) rc = go(umma_dw_kernel<5, 3>);
+  else rc = go(umma_dw_kernel<5, 5>);
   if (rc != GCL_OK) return rc;
   GCL_CHECK_LAUNCH("umma_dw");
   return GCL_OK;
