@@ -94,11 +94,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// hi = x with the mantissa cut to tf32's 10 bits (one LOP), lo = x - hi exactly (one FADD); the tensor
-// core ignores lo's low 13 bits, so hi + lo carries >= 20 mantissa bits of x (|err| < 2^-20 |x|).  The
-// cvt.rna.tf32 route costs ~5x the instructions and the loaders are issue-bound, not precision-bound.
+// hi = x rounded to tf32's 10 mantissa bits (add half an ulp to the bit pattern, then mask: round to
+// nearest, ties away, in two integer ops), lo = x - hi exactly (one FADD, either sign).  The tensor core
+// ignores lo's low 13 bits, so hi + lo carries ~21-22 mantissa bits of x and the dropped lo*lo term has no
+// preferred sign.  (Plain truncation is one op cheaper but biases every product low by ~1e-6; cvt.rna.tf32
+// gives the same values at ~4x the instructions, and the loaders are issue-bound.)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   lo = x - hi;
 }
 __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float4 v) {

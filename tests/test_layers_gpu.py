@@ -306,3 +306,36 @@ def test_error_paths():
         ops.linear(x.double(), torch.randn(8, 8, device=DEV).double())
     with pytest.raises(ValueError):
         ops.linear(x, torch.randn(8, 9, device=DEV))
+
+
+@pytest.mark.parametrize("R,cin,cout", [(2048, 64, 64), (5000, 128, 128), (3000, 72, 48), (2500, 66, 64), (2500, 64, 33),
+                                         (3333, 30, 48), (2100, 96, 15), (40000, 128, 64), (100001, 64, 64), (4099, 96, 96)])
+def test_linear_tcgen05_3xtf32_path(R, cin, cout):
+    """rows >= 2048 run on the tcgen05 tensor cores in 3xTF32 (hi/lo split, fp32 accumulate in TMEM): forward
+    with bias + PReLU + pre-activation copy, dX and dW/db against fp64, and against the FFMA engine."""
+    from gcl_b200 import _cabi, ops
+    lib = _cabi.load()
+    gen = torch.Generator().manual_seed(R + cout)
+    x = torch.randn(R, cin, generator=gen).to(DEV)
+    W = (torch.randn(cout, cin, generator=gen) / cin ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=gen).to(DEV)
+    a = torch.tensor([0.25], device=DEV)
+    dy = torch.randn(R, cout, generator=gen).to(DEV)
+    pre = torch.nn.functional.linear(x.double(), W.double(), b.double())
+    want = dict(y=torch.where(pre > 0, pre, 0.25 * pre), z=pre, dx=dy.double() @ W.double(),
+                dW=dy.double().T @ x.double(), db=dy.double().sum(0))
+    got = {}
+    try:
+        for mode, tag in ((0, "tc"), (1, "ffma")):
+            assert lib.gcl_set_dense_mode(mode) == 0
+            y, z = ops.linear_fwd_raw(x, W, b, a, True)
+            dW, db = ops.linear_bwd_dw_raw(dy, x, True)
+            got[tag] = dict(y=y, z=z, dx=ops.linear_bwd_dx_raw(dy, W), dW=dW, db=db)
+    finally:
+        lib.gcl_set_dense_mode(0)
+    for k, ref in want.items():
+        assert_close(got["tc"][k], ref.float(), 2e-5, f"tcgen05 {k} ({R},{cin},{cout})")
+        assert_close(got["ffma"][k], ref.float(), 2e-5, f"ffma {k} ({R},{cin},{cout})")
+    # deterministic: same bits on a second call
+    y2, _ = ops.linear_fwd_raw(x, W, b, a, True)
+    assert torch.equal(y2, got["tc"]["y"])

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import RTOL_F32, assert_close
+from helpers import RTOL_F32, assert_close, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -110,11 +110,34 @@ def _check_grads(mine, ref, tol, what):
     assert n > 0
 
 
+def _set_engine(engine):
+    from gcl_b200 import _cabi
+    _cabi.load().gcl_set_dense_mode(1 if engine == "ffma" else 0)
+
+
+@pytest.fixture(autouse=True)
+def _restore_dense_engine():
+    yield
+    _set_engine("tcgen05")
+
+
+@pytest.mark.parametrize("engine", ["ffma", "tcgen05"])
 @pytest.mark.parametrize("name", ALL)
-def test_forecast_step_and_gradients_full_size(name):
-    """One forecast step (fwd), lat-weighted loss and all gradients at the BASELINE sizes, B = 1."""
+def test_forecast_step_and_gradients_full_size(name, engine):
+    """One forecast step (fwd), lat-weighted loss and all gradients at the BASELINE sizes, B = 1.
+
+    engine = ffma   : CUDA-core dense kernels; same fp32 operation mix as the reference, so outputs AND
+                      gradients must match the fp32 oracle within rel 1e-4.
+    engine = tcgen05: 3xTF32 tensor-core dense kernels (the default).  The forecast step must match the fp32
+                      oracle within rel 1e-4.  For the gradients the fp32 oracle is itself 1e-4..2e-3 away
+                      from the fp64 result on these models (PReLU kinks, long reductions -- measured, see
+                      DESIGN.md "Parity"), and a different-but-equally-accurate fp32 evaluation lands
+                      elsewhere inside that band; so each gradient is compared with the fp64 oracle and must
+                      be within max(1e-4, 3 x the fp32 oracle's own distance from fp64)."""
+    import copy
     from gcl_b200.train import Trainer
     from oracle import model as om
+    _set_engine(engine)
     mine, ref, cfg, nlat, nlon = _models(name)
     G = nlat * nlon
     F, T = cfg["data"]["num_features_used"], cfg["data"]["obs_window_used"]
@@ -129,10 +152,30 @@ def test_forecast_step_and_gradients_full_size(name):
     tr.zero_grad()
     lg = tr.loss(X.to(DEV), y.to(DEV), 0.0, **kw)
     lg.backward()
-    lc = om.training_loss(ref, X, y, 1, om.lat_weights(nlat, nlon), **kw)
+    lw = om.lat_weights(nlat, nlon)
+    lc = om.training_loss(ref, X, y, 1, lw, **kw)
     lc.backward()
-    assert abs(float(lg) - float(lc)) <= RTOL_F32 * abs(float(lc)), (float(lg), float(lc))
-    _check_grads(mine, ref, RTOL_F32, name)
+    assert abs(float(lg.detach()) - float(lc.detach())) <= RTOL_F32 * abs(float(lc.detach()))
+    if engine == "ffma":
+        _check_grads(mine, ref, RTOL_F32, name)
+        return
+    ref64 = copy.deepcopy(ref).double()
+    ref64.zero_grad()
+    ref64.init_grid_features, ref64.init_mesh_features = ref64.init_grid_features.double(), ref64.init_mesh_features.double()
+    om.training_loss(ref64, X.double(), y.double(), 1, lw.double(), **kw).backward()
+    p32, p64 = dict(ref.named_parameters()), dict(ref64.named_parameters())
+    checked = 0
+    for k, p in mine.named_parameters():
+        if p64[k].grad is None:
+            continue
+        truth = p64[k].grad.float()
+        ref_err = rel_err(p32[k].grad, truth)
+        got_err = rel_err(p.grad, truth)
+        if float((p.grad.detach().cpu() - truth).abs().max()) <= 1e-9:
+            continue
+        assert got_err <= max(RTOL_F32, 3 * ref_err), f"{name} d{k}: {got_err:.2e} vs fp64 (fp32 oracle: {ref_err:.2e})"
+        checked += 1
+    assert checked > 0
 
 
 @pytest.mark.parametrize("name", ["baseline", "attention", "sparse_attention"])
@@ -195,7 +238,7 @@ def test_batched_equals_per_sample_and_ar_rollout():
     out_b = mine(X=X.to(DEV))
     assert out_b.shape == (3, G, F)
     for b in range(3):
-        assert_close(out_b[b], mine(X=X[b:b + 1].to(DEV)), 1e-6, "batched vs single")
+        assert_close(out_b[b], mine(X=X[b:b + 1].to(DEV)), 2e-5, "batched vs single")   # FFMA (< 2048 rows) vs tcgen05 engine
     assert_close(out_b, ref(X=X), RTOL_F32, "batched vs oracle")
     tr = Trainer(mine, nlat, nlon, ar_steps=2)
     tr.zero_grad()
