@@ -53,228 +53,397 @@ struct W<1> {
   static __device__ __forceinline__ T xor_add(T a, int o) { return a + __shfl_xor_sync(0xffffffffu, a, o); }
 };
 
-// a_src[row,h] = <z[row,h,:], att_src[h,:]>, same for dst.  One warp per row.
+// a_src[row,h] = <z[row,h,:], att_src[h,:]>, same for dst.  8 lanes per (row, head), 128-bit loads.
 __global__ void gat_scores_kernel(const float* __restrict__ z, const float* __restrict__ att_src,
                                   const float* __restrict__ att_dst, float* __restrict__ a_src,
                                   float* __restrict__ a_dst, int64_t rows, int H, int C) {
-  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float* zr = z + row * H * C;
-  for (int h = 0; h < H; ++h) {
-    float s = 0.f, d = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float v = zr[h * C + c];
-      s = fmaf(v, __ldg(att_src + h * C + c), s);
-      d = fmaf(v, __ldg(att_dst + h * C + c), d);
+  const int64_t item = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;   // (row, head)
+  const int gl = threadIdx.x & 7;
+  const unsigned mask = 0xffu << ((threadIdx.x & 31) & ~7);
+  if (item >= rows * H) return;
+  const int h = (int)(item % H);
+  const float* zr = z + item * C;
+  const float* as = att_src + (int64_t)h * C;
+  const float* ad = att_dst + (int64_t)h * C;
+  float s = 0.f, d = 0.f;
+  if ((C & 3) == 0 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(att_src) |
+                        reinterpret_cast<uintptr_t>(att_dst)) & 15) == 0) {
+    for (int c = gl * 4; c < C; c += 32) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(zr + c));
+      const float4 p = __ldg(reinterpret_cast<const float4*>(as + c));
+      const float4 q = __ldg(reinterpret_cast<const float4*>(ad + c));
+      s += v.x * p.x + v.y * p.y + v.z * p.z + v.w * p.w;
+      d += v.x * q.x + v.y * q.y + v.z * q.z + v.w * q.w;
     }
-    s = warp_sum(s);
-    d = warp_sum(d);
-    if (lane == 0) {
-      a_src[row * H + h] = s;
-      a_dst[row * H + h] = d;
+  } else {
+    for (int c = gl; c < C; c += 8) {
+      const float v = zr[c];
+      s = fmaf(v, __ldg(as + c), s);
+      d = fmaf(v, __ldg(ad + c), d);
     }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(mask, s, o, 8);
+    d += __shfl_xor_sync(mask, d, o, 8);
+  }
+  if (gl == 0) {
+    a_src[item] = s;
+    a_dst[item] = d;
   }
 }
 
-template <int VW, int L>
-__global__ void __launch_bounds__(kWarps * 32)
+// ---- shared structure of the three attention kernels -------------------------------------------------
+// A group of L lanes (L = 4..32 >= words per head slice) owns one (row, SB consecutive samples); 32/L
+// groups share a warp and use per-group shuffle masks.  The row's neighbour ids are fetched once and
+// reused for all SB samples and heads; every edge issues SB independent 128-bit gathers per lane, which
+// is what keeps enough bytes in flight (the per-sample-per-warp version of these kernels ran at ~10% of
+// the HBM roofline, latency-bound).
+template <int L>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+  return (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << ((lane / L) * L));
+}
+template <int L>
+__device__ __forceinline__ float gsum(float v, unsigned mask) {
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, L);
+  return v;
+}
+template <int L>
+__device__ __forceinline__ float gmax(float v, unsigned mask) {
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o, L));
+  return v;
+}
+
+template <int VW, int L, int SB>
+__global__ void __launch_bounds__(kWarps * 32, 3)
     gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                    const int32_t* __restrict__ perm, const float* __restrict__ z, const float* __restrict__ a_src,
                    const float* __restrict__ a_dst, const float* __restrict__ bias, float* __restrict__ out,
-                   float* __restrict__ alpha_csr, float* __restrict__ alpha_pyg, int64_t N, int64_t nnz, int H,
+                   float* __restrict__ alpha_csr, float* __restrict__ alpha_pyg, int64_t N, int64_t nnz, int B, int H,
                    int C, int concat, float slope) {
   using V = W<VW>;
-  constexpr int S = 32 / L;
+  constexpr int kGroups = 32 / L;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gl = lane & (L - 1), slot = lane / L;
-  const int64_t i = (int64_t)blockIdx.x * kWarps + warp;
-  const int64_t b = blockIdx.y;
+  const int gl = lane & (L - 1);
+  const unsigned mask = group_mask<L>(lane);
+  const int64_t i = ((int64_t)blockIdx.x * kWarps + warp) * kGroups + lane / L;
   if (i >= N) return;
+  const int b0 = blockIdx.y * SB;
+  const int nb = min(SB, B - b0);
   const int32_t beg = rowptr[i], end = rowptr[i + 1];
   const int HC = H * C, Cout = concat ? HC : C;
-  const int64_t nb = b * N;
-  const float* zb = z + nb * HC;
-  const int words = (C + VW - 1) / VW;  // words per head slice
-  const int nchunks = (words + L - 1) / L;
-  const float inv_h = 1.f / (float)H;
+  const int words = (C + VW - 1) / VW, nchunks = (words + L - 1) / L;
+  const float hscale = concat ? 1.f : 1.f / (float)H;     // head mean folded into the attention weight
+  const bool single = (end - beg) <= L;                   // whole row in one pass of the group's lanes
 
   for (int chunk = 0; chunk < nchunks; ++chunk) {
     const int off = (chunk * L + gl) * VW;
     const bool live = off < C;
-    typename V::T total = V::zero();
-    for (int h = 0; h < H; ++h) {
-      const float adi = a_dst[(nb + i) * H + h];
-      float m = -INFINITY;
-      for (int32_t k = beg + lane; k < end; k += 32)
-        m = fmaxf(m, leaky(a_src[(nb + col[k]) * H + h] + adi, slope));
-      m = warp_max(m);
-      float ssum = 0.f;
-      for (int32_t k = beg + lane; k < end; k += 32)
-        ssum += expf(leaky(a_src[(nb + col[k]) * H + h] + adi, slope) - m);
-      ssum = warp_sum(ssum) + 1e-16f;
-
-      typename V::T acc = V::zero();
-      for (int32_t base = beg; base < end; base += 32) {
-        const int32_t k = base + lane;
-        const int n = min(32, end - base);
-        int32_t c_reg = 0;
-        float a_reg = 0.f;
-        if (k < end) {
-          c_reg = col[k];
-          a_reg = expf(leaky(a_src[(nb + c_reg) * H + h] + adi, slope) - m) / ssum;
-          if (chunk == 0) {
-            alpha_csr[(b * nnz + k) * H + h] = a_reg;
-            if (alpha_pyg) alpha_pyg[(b * nnz + perm[k]) * H + h] = a_reg;
-          }
-        }
-        for (int jj = 0; jj < n; jj += S) {
-          const int j = jj + slot;
-          const int src = j < n ? j : 0;
-          const int32_t c = __shfl_sync(0xffffffffu, c_reg, src);
-          const float a = __shfl_sync(0xffffffffu, a_reg, src);
-          if (j < n && live) V::fma(acc, a, V::load(zb + (int64_t)c * HC + h * C + off));
-        }
-      }
+    typename V::T acc[SB];
 #pragma unroll
-      for (int o = L; o < 32; o <<= 1) acc = V::xor_add(acc, o);
-      if (concat) {
-        if (live && slot == 0) {
-          if (bias) acc = V::add(acc, V::load(bias + h * C + off));
-          V::store(out + (nb + i) * Cout + h * C + off, acc);
+    for (int s = 0; s < SB; ++s) acc[s] = V::zero();
+    for (int h = 0; h < H; ++h) {
+      float adi[SB], m[SB], rl[SB];
+#pragma unroll
+      for (int s = 0; s < SB; ++s) adi[s] = (s < nb) ? a_dst[((int64_t)(b0 + s) * N + i) * H + h] : 0.f;
+      float e_own[SB];                                     // single-pass rows: this lane's edge logit
+      const int32_t k_own = beg + gl;
+      const int32_t c_own = (single && k_own < end) ? col[k_own] : 0;
+      if (single) {
+        // lane k holds edge k: max and sum are two group reductions, one exp per edge
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+          e_own[s] = (s < nb && k_own < end) ? leaky(a_src[((int64_t)(b0 + s) * N + c_own) * H + h] + adi[s], slope)
+                                             : -INFINITY;
+          m[s] = gmax<L>(e_own[s], mask);
+          e_own[s] = (k_own < end && s < nb) ? __expf(e_own[s] - m[s]) : 0.f;
+          rl[s] = 1.f / (gsum<L>(e_own[s], mask) + 1e-16f);
         }
       } else {
-        total = V::add(total, acc);
+        float l[SB];
+#pragma unroll
+        for (int s = 0; s < SB; ++s) { m[s] = -INFINITY; l[s] = 0.f; }
+        for (int32_t k = beg + gl; k < end; k += L) {        // online (max, sum) per sample over long rows
+          const int32_t c = col[k];
+#pragma unroll
+          for (int s = 0; s < SB; ++s) {
+            if (s < nb) {
+              const float e = leaky(a_src[((int64_t)(b0 + s) * N + c) * H + h] + adi[s], slope);
+              const float mn = fmaxf(m[s], e);
+              l[s] = l[s] * __expf(m[s] - mn) + __expf(e - mn);
+              m[s] = mn;
+            }
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+          const float mg = gmax<L>(m[s], mask);
+          rl[s] = 1.f / (gsum<L>(m[s] == -INFINITY ? 0.f : l[s] * __expf(m[s] - mg), mask) + 1e-16f);
+          m[s] = mg;
+        }
+      }
+      for (int32_t base = beg; base < end; base += L) {
+        const int32_t k = base + gl;
+        const int n = min(L, end - base);
+        int32_t c_reg = 0;
+        float a_reg[SB];
+#pragma unroll
+        for (int s = 0; s < SB; ++s) a_reg[s] = 0.f;
+        if (k < end) {
+          c_reg = single ? c_own : col[k];
+          const int32_t pk = (alpha_pyg && chunk == 0) ? perm[k] : 0;
+#pragma unroll
+          for (int s = 0; s < SB; ++s) {
+            if (s < nb) {
+              float p;
+              if (single) p = e_own[s];
+              else p = __expf(leaky(a_src[((int64_t)(b0 + s) * N + c_reg) * H + h] + adi[s], slope) - m[s]);
+              const float al = p * rl[s];
+              a_reg[s] = al * hscale;
+              if (chunk == 0) {
+                alpha_csr[((int64_t)(b0 + s) * nnz + k) * H + h] = al;
+                if (alpha_pyg) alpha_pyg[((int64_t)(b0 + s) * nnz + pk) * H + h] = al;
+              }
+            }
+          }
+        }
+#pragma unroll 2
+        for (int j = 0; j < n; ++j) {
+          const int32_t c = __shfl_sync(mask, c_reg, j, L);
+          float a[SB];
+#pragma unroll
+          for (int s = 0; s < SB; ++s) a[s] = __shfl_sync(mask, a_reg[s], j, L);
+          if (live) {
+            typename V::T v[SB];
+#pragma unroll
+            for (int s = 0; s < SB; ++s)
+              if (s < nb) v[s] = V::load(z + ((int64_t)(b0 + s) * N + c) * HC + h * C + off);
+#pragma unroll
+            for (int s = 0; s < SB; ++s)
+              if (s < nb) V::fma(acc[s], a[s], v[s]);
+          }
+        }
+      }
+      if (concat && live) {
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+          if (s < nb) {
+            typename V::T o = acc[s];
+            if (bias) o = V::add(o, V::load(bias + h * C + off));
+            V::store(out + ((int64_t)(b0 + s) * N + i) * Cout + h * C + off, o);
+          }
+          acc[s] = V::zero();
+        }
       }
     }
-    if (!concat && live && slot == 0) {
-      total = V::scale(total, inv_h);
-      if (bias) total = V::add(total, V::load(bias + off));
-      V::store(out + (nb + i) * Cout + off, total);
+    if (!concat && live) {
+#pragma unroll
+      for (int s = 0; s < SB; ++s) {
+        if (s < nb) {
+          typename V::T o = acc[s];
+          if (bias) o = V::add(o, V::load(bias + off));
+          V::store(out + ((int64_t)(b0 + s) * N + i) * Cout + off, o);
+        }
+      }
     }
   }
 }
 
-// Backward pass 1, one warp per (sample, receiver i):
+// Backward pass 1, group per (receiver i, SB samples):
 //   dalpha_k = <do_h(i), z[col_k, h]>;  t = sum_k alpha_k dalpha_k;  g_k = alpha_k (dalpha_k - t) * LeakyReLU'
 //   g_csr[b,k,h] = g_k;  da_dst[b,i,h] = sum_k g_k
-template <int VW, int L>
-__global__ void __launch_bounds__(kWarps * 32)
+template <int VW, int L, int SB>
+__global__ void __launch_bounds__(kWarps * 32, 3)
     gat_bwd_dst_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const float* __restrict__ z, const float* __restrict__ a_src,
                        const float* __restrict__ a_dst, const float* __restrict__ alpha_csr,
                        const float* __restrict__ dout, float* __restrict__ g_csr, float* __restrict__ da_dst,
-                       int64_t N, int64_t nnz, int H, int C, int concat, float slope) {
+                       int64_t N, int64_t nnz, int B, int H, int C, int concat, float slope) {
   using V = W<VW>;
-  constexpr int S = 32 / L;
+  constexpr int kGroups = 32 / L;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gl = lane & (L - 1), slot = lane / L;
-  const int64_t i = (int64_t)blockIdx.x * kWarps + warp;
-  const int64_t b = blockIdx.y;
+  const int gl = lane & (L - 1);
+  const unsigned mask = group_mask<L>(lane);
+  const int64_t i = ((int64_t)blockIdx.x * kWarps + warp) * kGroups + lane / L;
   if (i >= N) return;
+  const int b0 = blockIdx.y * SB;
+  const int nb = min(SB, B - b0);
   const int32_t beg = rowptr[i], end = rowptr[i + 1];
   const int HC = H * C, Cout = concat ? HC : C;
-  const int64_t nb = b * N;
-  const float* zb = z + nb * HC;
-  const int words = (C + VW - 1) / VW;
-  const int nchunks = (words + L - 1) / L;
+  const int words = (C + VW - 1) / VW, nchunks = (words + L - 1) / L;
   const float hs = concat ? 1.f : 1.f / (float)H;
+  const bool single = (end - beg) <= L;    // the whole row fits one pass: dalpha stays in registers
 
   for (int h = 0; h < H; ++h) {
-    // dalpha_k for every entry of the row (S entries at a time), parked in g_csr
-    for (int32_t base = beg; base < end; base += S) {
-      const int32_t k = base + slot;
-      const bool valid = k < end;
-      const int32_t c = valid ? col[k] : 0;
-      float d = 0.f;
-      for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int off = (chunk * L + gl) * VW;
-        if (valid && off < C) {
-          const typename V::T dv = V::load(dout + (nb + i) * Cout + (concat ? h * C : 0) + off);
-          d += V::dot(dv, V::load(zb + (int64_t)c * HC + h * C + off));
+    float keep[SB], t[SB];
+#pragma unroll
+    for (int s = 0; s < SB; ++s) keep[s] = t[s] = 0.f;
+    for (int32_t base = beg; base < end; base += L) {
+      const int n = min(L, end - base);
+      const int32_t k = base + gl;
+      const int32_t c_reg = (k < end) ? col[k] : 0;
+      float mine[SB];
+#pragma unroll
+      for (int s = 0; s < SB; ++s) mine[s] = 0.f;
+      for (int j = 0; j < n; ++j) {
+        const int32_t c = __shfl_sync(mask, c_reg, j, L);
+        float d[SB];
+#pragma unroll
+        for (int s = 0; s < SB; ++s) d[s] = 0.f;
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+          const int off = (chunk * L + gl) * VW;
+          if (off < C) {
+            typename V::T zv[SB], dv[SB];
+#pragma unroll
+            for (int s = 0; s < SB; ++s) {
+              if (s < nb) {
+                zv[s] = V::load(z + ((int64_t)(b0 + s) * N + c) * HC + h * C + off);
+                dv[s] = V::load(dout + ((int64_t)(b0 + s) * N + i) * Cout + (concat ? h * C : 0) + off);
+              }
+            }
+#pragma unroll
+            for (int s = 0; s < SB; ++s)
+              if (s < nb) d[s] += V::dot(dv[s], zv[s]);
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+          const float r = gsum<L>(d[s], mask) * hs;
+          if (gl == j) mine[s] = r;
         }
       }
+      if (k < end) {
 #pragma unroll
-      for (int o = L / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-      if (valid && gl == 0) g_csr[(b * nnz + k) * H + h] = d * hs;
+        for (int s = 0; s < SB; ++s) {
+          if (s < nb) {
+            const int64_t idx = ((int64_t)(b0 + s) * nnz + k) * H + h;
+            t[s] += alpha_csr[idx] * mine[s];
+            if (single) keep[s] = mine[s];
+            else g_csr[idx] = mine[s];
+          }
+        }
+      }
     }
-    __syncwarp();
-    const float adi = a_dst[(nb + i) * H + h];
-    float t = 0.f;
-    for (int32_t k = beg + lane; k < end; k += 32)
-      t += alpha_csr[(b * nnz + k) * H + h] * g_csr[(b * nnz + k) * H + h];
-    t = warp_sum(t);
-    float gs = 0.f;
-    for (int32_t k = beg + lane; k < end; k += 32) {
-      const int64_t idx = (b * nnz + k) * H + h;
-      const float pre = a_src[(nb + col[k]) * H + h] + adi;
-      const float g = alpha_csr[idx] * (g_csr[idx] - t) * (pre > 0.f ? 1.f : slope);
-      g_csr[idx] = g;
-      gs += g;
+#pragma unroll
+    for (int s = 0; s < SB; ++s) t[s] = gsum<L>(t[s], mask);
+    float gs[SB];
+#pragma unroll
+    for (int s = 0; s < SB; ++s) gs[s] = 0.f;
+    for (int32_t k = beg + gl; k < end; k += L) {
+      const int32_t c = col[k];
+#pragma unroll
+      for (int s = 0; s < SB; ++s) {
+        if (s < nb) {
+          const int64_t idx = ((int64_t)(b0 + s) * nnz + k) * H + h;
+          const float dal = single ? keep[s] : g_csr[idx];   // own write (same lane <-> same entry)
+          const float pre = a_src[((int64_t)(b0 + s) * N + c) * H + h] + a_dst[((int64_t)(b0 + s) * N + i) * H + h];
+          const float g = alpha_csr[idx] * (dal - t[s]) * (pre > 0.f ? 1.f : slope);
+          g_csr[idx] = g;
+          gs[s] += g;
+        }
+      }
     }
-    gs = warp_sum(gs);
-    if (lane == 0) da_dst[(nb + i) * H + h] = gs;
-    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < SB; ++s) {
+      const float r = gsum<L>(gs[s], mask);
+      if (gl == 0 && s < nb) da_dst[((int64_t)(b0 + s) * N + i) * H + h] = r;
+    }
   }
 }
 
-// Backward pass 2, one warp per (sample, sender j), sender-grouped CSR:
+// Backward pass 2, group per (sender j, SB samples), sender-grouped CSR:
 //   da_src[b,j,h] = sum_k g_k ;  dz[b,j,h,:] = sum_k alpha_k do_h(i_k) + da_src att_src[h] + da_dst att_dst[h]
-template <int VW, int L>
-__global__ void __launch_bounds__(kWarps * 32)
+template <int VW, int L, int SB>
+__global__ void __launch_bounds__(kWarps * 32, 3)
     gat_bwd_src_kernel(const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
                        const int32_t* __restrict__ t2r, const float* __restrict__ alpha_csr,
                        const float* __restrict__ g_csr, const float* __restrict__ att_src,
                        const float* __restrict__ att_dst, const float* __restrict__ dout,
                        const float* __restrict__ da_dst, float* __restrict__ da_src, float* __restrict__ dz,
-                       int64_t N, int64_t nnz, int H, int C, int concat) {
+                       int64_t N, int64_t nnz, int B, int H, int C, int concat) {
   using V = W<VW>;
-  constexpr int S = 32 / L;
+  constexpr int kGroups = 32 / L;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gl = lane & (L - 1), slot = lane / L;
-  const int64_t jn = (int64_t)blockIdx.x * kWarps + warp;
-  const int64_t b = blockIdx.y;
+  const int gl = lane & (L - 1);
+  const unsigned mask = group_mask<L>(lane);
+  const int64_t jn = ((int64_t)blockIdx.x * kWarps + warp) * kGroups + lane / L;
   if (jn >= N) return;
+  const int b0 = blockIdx.y * SB;
+  const int nb = min(SB, B - b0);
   const int32_t beg = rowptr_t[jn], end = rowptr_t[jn + 1];
   const int HC = H * C, Cout = concat ? HC : C;
-  const int64_t nb = b * N;
-  const int words = (C + VW - 1) / VW;
-  const int nchunks = (words + L - 1) / L;
+  const int words = (C + VW - 1) / VW, nchunks = (words + L - 1) / L;
   const float hs = concat ? 1.f : 1.f / (float)H;
 
   for (int h = 0; h < H; ++h) {
-    float gs = 0.f;
-    for (int32_t k = beg + lane; k < end; k += 32) gs += g_csr[(b * nnz + t2r[k]) * H + h];
-    gs = warp_sum(gs);
-    if (lane == 0) da_src[(nb + jn) * H + h] = gs;
-    const float dad = da_dst[(nb + jn) * H + h];
+    float gsv[SB];
+#pragma unroll
+    for (int s = 0; s < SB; ++s) gsv[s] = 0.f;
+    for (int32_t k = beg + gl; k < end; k += L) {
+      const int32_t kr = t2r[k];
+#pragma unroll
+      for (int s = 0; s < SB; ++s)
+        if (s < nb) gsv[s] += g_csr[((int64_t)(b0 + s) * nnz + kr) * H + h];
+    }
+    float dad[SB];
+#pragma unroll
+    for (int s = 0; s < SB; ++s) {
+      gsv[s] = gsum<L>(gsv[s], mask);
+      dad[s] = 0.f;
+      if (s < nb) {
+        dad[s] = da_dst[((int64_t)(b0 + s) * N + jn) * H + h];
+        if (gl == 0) da_src[((int64_t)(b0 + s) * N + jn) * H + h] = gsv[s];
+      }
+    }
     for (int chunk = 0; chunk < nchunks; ++chunk) {
       const int off = (chunk * L + gl) * VW;
       const bool live = off < C;
-      typename V::T acc = V::zero();
-      for (int32_t base = beg; base < end; base += 32) {
-        const int32_t k = base + lane;
-        const int n = min(32, end - base);
+      typename V::T acc[SB];
+#pragma unroll
+      for (int s = 0; s < SB; ++s) acc[s] = V::zero();
+      for (int32_t base = beg; base < end; base += L) {
+        const int32_t k = base + gl;
+        const int n = min(L, end - base);
         int32_t i_reg = 0;
-        float a_reg = 0.f;
+        float a_reg[SB];
+#pragma unroll
+        for (int s = 0; s < SB; ++s) a_reg[s] = 0.f;
         if (k < end) {
           i_reg = col_t[k];
-          a_reg = alpha_csr[(b * nnz + t2r[k]) * H + h] * hs;
+          const int32_t kr = t2r[k];
+#pragma unroll
+          for (int s = 0; s < SB; ++s)
+            if (s < nb) a_reg[s] = alpha_csr[((int64_t)(b0 + s) * nnz + kr) * H + h] * hs;
         }
-        for (int jj = 0; jj < n; jj += S) {
-          const int j = jj + slot;
-          const int src = j < n ? j : 0;
-          const int32_t ii = __shfl_sync(0xffffffffu, i_reg, src);
-          const float a = __shfl_sync(0xffffffffu, a_reg, src);
-          if (j < n && live) V::fma(acc, a, V::load(dout + (nb + ii) * Cout + (concat ? h * C : 0) + off));
+#pragma unroll 2
+        for (int e = 0; e < n; ++e) {
+          const int32_t ii = __shfl_sync(mask, i_reg, e, L);
+          float a[SB];
+#pragma unroll
+          for (int s = 0; s < SB; ++s) a[s] = __shfl_sync(mask, a_reg[s], e, L);
+          if (live) {
+            typename V::T v[SB];
+#pragma unroll
+            for (int s = 0; s < SB; ++s)
+              if (s < nb) v[s] = V::load(dout + ((int64_t)(b0 + s) * N + ii) * Cout + (concat ? h * C : 0) + off);
+#pragma unroll
+            for (int s = 0; s < SB; ++s)
+              if (s < nb) V::fma(acc[s], a[s], v[s]);
+          }
         }
       }
+      if (live) {
+        const typename V::T as = V::load(att_src + h * C + off), ad = V::load(att_dst + h * C + off);
 #pragma unroll
-      for (int o = L; o < 32; o <<= 1) acc = V::xor_add(acc, o);
-      if (live && slot == 0) {
-        V::fma(acc, gs, V::load(att_src + h * C + off));
-        V::fma(acc, dad, V::load(att_dst + h * C + off));
-        V::store(dz + (nb + jn) * HC + h * C + off, acc);
+        for (int s = 0; s < SB; ++s) {
+          if (s < nb) {
+            V::fma(acc[s], gsv[s], as);
+            V::fma(acc[s], dad[s], ad);
+            V::store(dz + ((int64_t)(b0 + s) * N + jn) * HC + h * C + off, acc[s]);
+          }
+        }
       }
     }
   }
@@ -360,27 +529,38 @@ inline int pick_l(int words) { return words <= 4 ? 4 : words <= 8 ? 8 : words <=
 
 using namespace gcl;
 
-#define GAT_DISPATCH(VWV, LV, KERNEL, ...)                                              \
-  do {                                                                                  \
-    if (VWV == 4) {                                                                     \
-      if (LV == 4) KERNEL<4, 4><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);              \
-      else if (LV == 8) KERNEL<4, 8><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);         \
-      else if (LV == 16) KERNEL<4, 16><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);       \
-      else KERNEL<4, 32><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);                     \
-    } else {                                                                            \
-      if (LV == 4) KERNEL<1, 4><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);              \
-      else if (LV == 8) KERNEL<1, 8><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);         \
-      else if (LV == 16) KERNEL<1, 16><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);       \
-      else KERNEL<1, 32><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);                     \
-    }                                                                                   \
+#define GAT_DISPATCH_L(VWC, SBC, LV, KERNEL, ...)                                        \
+  do {                                                                                    \
+    if (LV == 4) KERNEL<VWC, 4, SBC><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);           \
+    else if (LV == 8) KERNEL<VWC, 8, SBC><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);      \
+    else if (LV == 16) KERNEL<VWC, 16, SBC><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);    \
+    else KERNEL<VWC, 32, SBC><<<grid, kWarps * 32, 0, s>>>(__VA_ARGS__);                  \
   } while (0)
+#define GAT_DISPATCH(VWV, SBV, LV, KERNEL, ...)                                            \
+  do {                                                                                    \
+    if (VWV == 4) {                                                                       \
+      if (SBV == 4) GAT_DISPATCH_L(4, 4, LV, KERNEL, __VA_ARGS__);                        \
+      else if (SBV == 2) GAT_DISPATCH_L(4, 2, LV, KERNEL, __VA_ARGS__);                   \
+      else GAT_DISPATCH_L(4, 1, LV, KERNEL, __VA_ARGS__);                                 \
+    } else {                                                                              \
+      GAT_DISPATCH_L(1, 1, LV, KERNEL, __VA_ARGS__);                                      \
+    }                                                                                     \
+  } while (0)
+
+// samples per lane group (the scalar VW = 1 fallback keeps one)
+static int gat_pick_sb(int vw, int64_t B, int64_t N, int64_t HC) {
+  if (vw != 4) return 1;
+  int sb = 4;
+  while (sb > 1 && (sb > B || sb * N * HC * 4 > (48ll << 20))) sb >>= 1;
+  return sb;
+}
 
 extern "C" int gcl_gat_scores_f32(const float* z, const float* att_src, const float* att_dst, float* a_src,
                                   float* a_dst, int64_t rows, int64_t heads, int64_t c, void* stream) {
   GCL_CHECK_ARG(z && att_src && att_dst && a_src && a_dst && rows >= 0 && heads > 0 && c > 0,
                 "gcl_gat_scores_f32: bad argument");
   if (rows == 0) return GCL_OK;
-  gat_scores_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  gat_scores_kernel<<<(unsigned)ceil_div(rows * heads * 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       z, att_src, att_dst, a_src, a_dst, rows, (int)heads, (int)c);
   GCL_CHECK_LAUNCH("gcl_gat_scores_f32");
   return GCL_OK;
@@ -398,9 +578,10 @@ extern "C" int gcl_gat_fwd_f32(const int32_t* rowptr, const int32_t* col, const 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int vw = (c % 4 == 0 && al16(z) && al16(out) && (!bias || al16(bias))) ? 4 : 1;
   const int l = pick_l((int)ceil_div(c, vw));
-  dim3 grid((unsigned)ceil_div(n_nodes, kWarps), (unsigned)batch);
-  GAT_DISPATCH(vw, l, gat_fwd_kernel, rowptr, col, perm, z, a_src, a_dst, bias, out, alpha_csr, alpha_pyg, n_nodes,
-               nnz, (int)heads, (int)c, concat, negative_slope);
+  const int sb = gat_pick_sb(vw, batch, n_nodes, heads * c);
+  dim3 grid((unsigned)ceil_div(n_nodes, (int64_t)kWarps * (32 / l)), (unsigned)ceil_div(batch, sb));
+  GAT_DISPATCH(vw, sb, l, gat_fwd_kernel, rowptr, col, perm, z, a_src, a_dst, bias, out, alpha_csr, alpha_pyg, n_nodes,
+               nnz, (int)batch, (int)heads, (int)c, concat, negative_slope);
   GCL_CHECK_LAUNCH("gcl_gat_fwd_f32");
   return GCL_OK;
 }
@@ -420,12 +601,13 @@ extern "C" int gcl_gat_bwd_f32(const int32_t* rowptr, const int32_t* col, const 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int vw = (c % 4 == 0 && al16(z) && al16(dout) && al16(dz) && al16(att_src) && al16(att_dst)) ? 4 : 1;
   const int l = pick_l((int)ceil_div(c, vw));
-  dim3 grid((unsigned)ceil_div(n_nodes, kWarps), (unsigned)batch);
-  GAT_DISPATCH(vw, l, gat_bwd_dst_kernel, rowptr, col, z, a_src, a_dst, alpha_csr, dout, g_csr, da_dst, n_nodes, nnz,
-               (int)heads, (int)c, concat, negative_slope);
+  const int sb = gat_pick_sb(vw, batch, n_nodes, heads * c);
+  dim3 grid((unsigned)ceil_div(n_nodes, (int64_t)kWarps * (32 / l)), (unsigned)ceil_div(batch, sb));
+  GAT_DISPATCH(vw, sb, l, gat_bwd_dst_kernel, rowptr, col, z, a_src, a_dst, alpha_csr, dout, g_csr, da_dst, n_nodes,
+               nnz, (int)batch, (int)heads, (int)c, concat, negative_slope);
   GCL_CHECK_LAUNCH("gcl_gat_bwd_f32(dst pass)");
-  GAT_DISPATCH(vw, l, gat_bwd_src_kernel, rowptr_t, col_t, t2r, alpha_csr, g_csr, att_src, att_dst, dout, da_dst,
-               da_src, dz, n_nodes, nnz, (int)heads, (int)c, concat);
+  GAT_DISPATCH(vw, sb, l, gat_bwd_src_kernel, rowptr_t, col_t, t2r, alpha_csr, g_csr, att_src, att_dst, dout, da_dst,
+               da_src, dz, n_nodes, nnz, (int)batch, (int)heads, (int)c, concat);
   GCL_CHECK_LAUNCH("gcl_gat_bwd_f32(src pass)");
   return GCL_OK;
 }
