@@ -42,6 +42,53 @@ __global__ void prelu_bwd_kernel(const float* __restrict__ dy, const float* __re
   }
 }
 
+// dx = dy * (x > 0 ? 1 : a) in one pass that ALSO produces the column sums of dx (the bias gradient of the
+// layer whose PReLU this is) and the slope gradient: part[blk][0..C) = column partials, part[blk][C] = slope.
+// Block (32, 8): lanes run along columns, 8 row lanes; each block owns a contiguous row range.
+__global__ void __launch_bounds__(256)
+    prelu_bwd_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                            const float* __restrict__ slope, float* __restrict__ dx, float* __restrict__ part,
+                            int64_t rows, int C, int64_t rows_per_block) {
+  __shared__ float sm[8][33];
+  __shared__ float ss[8];
+  const float a = __ldg(slope);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float sl = 0.f;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + tx;
+    float cs = 0.f;
+    if (c < C) {
+      for (int64_t r = r0 + ty; r < r1; r += 8) {
+        const float xv = x[r * C + c], g = dy[r * C + c];
+        const bool pos = xv > 0.f;
+        const float d = pos ? g : a * g;
+        dx[r * C + c] = d;
+        cs += d;
+        sl += pos ? 0.f : g * xv;
+      }
+    }
+    sm[ty][tx] = cs;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += sm[k][tx];
+      part[(int64_t)blockIdx.x * (C + 1) + c] = t;
+    }
+    __syncthreads();
+  }
+  sl = warp_sum(sl);
+  if (tx == 0) ss[ty] = sl;
+  __syncthreads();
+  if (tx == 0 && ty == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += ss[k];
+    part[(int64_t)blockIdx.x * (C + 1) + C] = t;
+  }
+}
+
 __global__ void sum_partials_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
   // one warp, fixed order: lane-strided partial sums then a shuffle tree
   float s = 0.f;
@@ -219,6 +266,35 @@ extern "C" int gcl_prelu_bwd_f32(const float* dy, const float* x, const float* s
   GCL_CHECK_LAUNCH("gcl_prelu_bwd_f32");
   sum_partials_kernel<<<1, 32, 0, s>>>(part, nblk, dslope);
   GCL_CHECK_LAUNCH("gcl_prelu_bwd_f32(reduce)");
+  return GCL_OK;
+}
+
+extern "C" size_t gcl_prelu_bwd_colsum_workspace_bytes(int64_t rows, int64_t c) {
+  if (rows < 0 || c <= 0) return 0;
+  return (size_t)ln_plan(rows).nblk * (size_t)(c + 1) * sizeof(float) + 256;
+}
+
+extern "C" int gcl_prelu_bwd_colsum_f32(const float* dy, const float* x, const float* slope, float* dx, float* dslope,
+                                        float* dbias, int64_t rows, int64_t c, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  GCL_CHECK_ARG(dy && x && slope && dx && dslope && dbias && workspace && rows >= 0 && c > 0 && c < (1 << 20),
+                "gcl_prelu_bwd_colsum_f32: bad argument");
+  if (workspace_bytes < gcl_prelu_bwd_colsum_workspace_bytes(rows, c)) {
+    set_error("gcl_prelu_bwd_colsum_f32: workspace too small");
+    return GCL_ERR_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rows == 0) {
+    cudaMemsetAsync(dslope, 0, sizeof(float), s);
+    cudaMemsetAsync(dbias, 0, sizeof(float) * c, s);
+    return GCL_OK;
+  }
+  LnPlan pl = ln_plan(rows);
+  float* part = static_cast<float*>(workspace);
+  prelu_bwd_colsum_kernel<<<pl.nblk, dim3(32, 8), 0, s>>>(dy, x, slope, dx, part, rows, (int)c, pl.rows_per_block);
+  GCL_CHECK_LAUNCH("gcl_prelu_bwd_colsum_f32");
+  reduce_cols_kernel<<<(unsigned)ceil_div(c + 1, 256), 256, 0, s>>>(part, pl.nblk, (int)c + 1, dbias, dslope, (int)c);
+  GCL_CHECK_LAUNCH("gcl_prelu_bwd_colsum_f32(reduce)");
   return GCL_OK;
 }
 

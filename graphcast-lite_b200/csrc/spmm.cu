@@ -111,10 +111,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 }
 
 // samples per lane group: as many as keep SB feature matrices resident in L2 (126 MB) together
-inline int pick_sb(int64_t B, int64_t n_rows, int64_t C) {
+// Graphs with < 4 entries per row (grid<->mesh: mostly the self loop) have almost no reuse to protect,
+// so they always take 8 samples per group.
+inline int pick_sb(int64_t B, int64_t n_rows, int64_t C, int64_t nnz) {
   const int64_t per_sample = n_rows * C * 4;
+  const bool low_reuse = nnz > 0 && nnz < 4 * n_rows;
   int sb = 8;
-  while (sb > 1 && (sb > B || sb * per_sample > (48ll << 20))) sb >>= 1;
+  while (sb > 1 && (sb > B || (!low_reuse && sb * per_sample > (48ll << 20)))) sb >>= 1;
   return sb;
 }
 
@@ -146,8 +149,8 @@ int dispatch_sb(int sb, const int32_t* rowptr, const int32_t* col, const float* 
 template <int VW>
 int dispatch_l(int64_t units, const int32_t* rowptr, const int32_t* col, const float* w, const float* x,
                float* out, int64_t B, int64_t n_rows, int64_t C, int64_t xbs, int64_t obs, const float* bias,
-               const float* slope, float* z_out, cudaStream_t s) {
-  const int sb = pick_sb(B, n_rows, C);
+               const float* slope, float* z_out, int64_t nnz, cudaStream_t s) {
+  const int sb = pick_sb(B, n_rows, C, nnz);
   if (units <= 4) return dispatch_sb<VW, 4>(sb, rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
   if (units <= 8) return dispatch_sb<VW, 8>(sb, rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
   if (units <= 16) return dispatch_sb<VW, 16>(sb, rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
@@ -162,7 +165,7 @@ using namespace gcl;
 extern "C" int gcl_spmm_f32(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, float* out,
                             int64_t batch, int64_t n_rows_out, int64_t channels, int64_t x_bstride,
                             int64_t out_bstride, const float* bias, const float* prelu_slope, float* z_out,
-                            void* stream) {
+                            int64_t nnz, void* stream) {
   GCL_CHECK_ARG(rowptr && col && x && out, "gcl_spmm_f32: null pointer argument");
   GCL_CHECK_ARG(x != out, "gcl_spmm_f32: x and out must not alias");
   GCL_CHECK_ARG(batch >= 0 && n_rows_out >= 0 && channels > 0 && channels < (1 << 20),
@@ -176,7 +179,7 @@ extern "C" int gcl_spmm_f32(const int32_t* rowptr, const int32_t* col, const flo
                    (!bias || al16(bias)) && (!z_out || al16(z_out));
   if (vec)
     return dispatch_l<4>(channels / 4, rowptr, col, w, x, out, batch, n_rows_out, channels, x_bstride,
-                         out_bstride, bias, prelu_slope, z_out, s);
+                         out_bstride, bias, prelu_slope, z_out, nnz, s);
   return dispatch_l<1>(channels, rowptr, col, w, x, out, batch, n_rows_out, channels, x_bstride, out_bstride,
-                       bias, prelu_slope, z_out, s);
+                       bias, prelu_slope, z_out, nnz, s);
 }

@@ -428,7 +428,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp > kEpiWarps) {
     const int lw = warp - (kEpiWarps + 1);                 // 0..6
     const int na_units = 8 * ((M + 31) / 32), nb_units = 8 * ((N + 31) / 32);
-    constexpr int kDepth = 2;
+    // register prefetch ring: as deep as the 168-register budget allows for this shape
+    constexpr int kDepth = (NAU + NBU <= 6) ? 4 : ((NAU + NBU <= 8) ? 3 : 2);
     float4 abuf[kDepth][NAU], bbuf[kDepth][NBU];
     // per-unit element offsets relative to the first row of a K-block (-1 = unit or column out of range)
     int offa[NAU], offb[NBU];

@@ -20,7 +20,7 @@ _PROTOS = {
     "gcl_csr_workspace_bytes": (SZ, [I64, I64]),
     "gcl_csr_build": (c_int, [P, P, I64, I64, I32, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
     "gcl_csr_weights": (c_int, [P, P, P, P, P, I64, I64, I32, P, P, P, P]),
-    "gcl_spmm_f32": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, P, P, P, P]),
+    "gcl_spmm_f32": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "gcl_linear_fwd_f32": (c_int, [P, P, P, P, I64, I64, I64, P, P, P, P]),
     "gcl_linear_bwd_dx_f32": (c_int, [P, P, P, I64, I64, I64, P, P]),
     "gcl_set_dense_mode": (c_int, [I32]),
@@ -32,6 +32,8 @@ _PROTOS = {
     "gcl_prelu_fwd_f32": (c_int, [P, P, P, I64, P]),
     "gcl_prelu_bwd_workspace_bytes": (SZ, [I64]),
     "gcl_prelu_bwd_f32": (c_int, [P, P, P, P, P, I64, P, SZ, P]),
+    "gcl_prelu_bwd_colsum_workspace_bytes": (SZ, [I64, I64]),
+    "gcl_prelu_bwd_colsum_f32": (c_int, [P, P, P, P, P, P, I64, I64, P, SZ, P]),
     "gcl_layernorm_fwd_f32": (c_int, [P, P, P, P, P, P, I64, I64, F32, P]),
     "gcl_layernorm_bwd_workspace_bytes": (SZ, [I64, I64]),
     "gcl_layernorm_bwd_f32": (c_int, [P, P, P, P, P, P, P, P, I64, I64, P, SZ, P]),

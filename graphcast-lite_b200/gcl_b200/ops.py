@@ -86,7 +86,7 @@ def spmm_raw(rowptr, col, w, x3, n_out, bias=None, slope=None, want_z=False):
         nnz = int(col.numel())
         nbytes = 4 * B * C * (n_in + n_out * (2 if want_z else 1)) + nnz * (8 if w is not None else 4) + 4 * (n_out + 1)
         _call("gcl_spmm_f32", _p(rowptr), _p(col), _p(w), _p(x3), _p(out), B, n_out, C, n_in * C, n_out * C,
-              _p(bias), _p(slope), _p(z), _stream(), nbytes=nbytes, tag=f"N{n_out}xC{C}xB{B}")
+              _p(bias), _p(slope), _p(z), nnz, _stream(), nbytes=nbytes, tag=f"N{n_out}xC{C}xB{B}")
     return out, z
 
 
@@ -112,6 +112,22 @@ def prelu_bwd_raw(dy, z, slope):
         _call("gcl_prelu_bwd_f32", _p(dy), _p(z), _p(slope), _p(dx), _p(dslope), n, _p(ws), nb, _stream(),
               nbytes=12 * n, tag=f"n{n}")
     return dx, dslope
+
+
+def prelu_bwd_colsum_raw(dy3, z, slope):
+    """(dx, dslope[1], dbias[C]) in one pass over dy / z."""
+    C = dy3.shape[-1]
+    R = dy3.numel() // C
+    dx = torch.empty_like(dy3)
+    dslope = torch.empty(1, dtype=torch.float32, device=dy3.device)
+    dbias = torch.empty(C, dtype=torch.float32, device=dy3.device)
+    lib = _cabi.load()
+    nb = lib.gcl_prelu_bwd_colsum_workspace_bytes(R, C)
+    ws = _ws(nb, dy3.device)
+    with torch.cuda.device(dy3.device):
+        _call("gcl_prelu_bwd_colsum_f32", _p(dy3), _p(z), _p(slope), _p(dx), _p(dslope), _p(dbias), R, C, _p(ws), nb,
+              _stream(), nbytes=12 * R * C, tag=f"R{R}xC{C}")
+    return dx, dslope, dbias
 
 
 def linear_fwd_raw(x2, W, bias=None, slope=None, want_z=False):
@@ -176,11 +192,16 @@ class _Aggregate(torch.autograd.Function):
         z, slope = ctx.saved_tensors
         g = ctx.graph
         d3, _ = _as3(_chk(dout, "grad_out"))
-        dslope = None
-        if ctx.has_slope:
+        dslope = dbias = None
+        want_bias = ctx.has_bias and ctx.needs_input_grad[1]
+        if ctx.has_slope and want_bias:
+            d3, dslope, dbias = prelu_bwd_colsum_raw(d3, z, slope)      # one pass instead of two
+            dslope = dslope.view_as(slope)
+        elif ctx.has_slope:
             d3, dslope = prelu_bwd_raw(d3, z, slope)
             dslope = dslope.view_as(slope)
-        dbias = colsum_raw(d3.view(-1, d3.shape[-1])) if ctx.has_bias and ctx.needs_input_grad[1] else None
+        elif want_bias:
+            dbias = colsum_raw(d3.view(-1, d3.shape[-1]))
         dx = None
         if ctx.needs_input_grad[0]:
             _, wt = g.weights(ctx.kind)

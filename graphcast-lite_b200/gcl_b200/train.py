@@ -82,8 +82,11 @@ class Trainer:
                 params.append(p)
         self.params = params
         dev = params[0].device
-        n = sum(p.numel() for p in params)
-        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        # every parameter starts on a 128-byte boundary of the flat buffer: the kernels take their 128-bit
+        # paths only for 16-byte aligned bias / attention vectors (padding stays 0 and gets 0 gradient)
+        ALIGN = 32
+        n = sum((p.numel() + ALIGN - 1) // ALIGN * ALIGN for p in params)
+        self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -94,8 +97,9 @@ class Trainer:
             self.flat_param[off:off + k].copy_(p.detach().reshape(-1))
             p.data = self.flat_param[off:off + k].view_as(p)
             p.grad = self.flat_grad[off:off + k].view_as(p)
-            off += k
-        self.num_params = n
+            off += (k + ALIGN - 1) // ALIGN * ALIGN
+        self.num_params = sum(p.numel() for p in params)     # trainable scalars (the reference's count)
+        self.flat_size = n                                   # incl. alignment padding
         self.lat_w = lat_weights(nlat, nlon, dev) if use_latitude_weighting else None
         self.G = nlat * nlon
         self._wsum = float(self.lat_w.sum()) if self.lat_w is not None else float(self.G)  # one-time sync
@@ -140,7 +144,7 @@ class Trainer:
         lib = _cabi.load()
         with torch.cuda.device(self.flat_param.device):
             _cabi.check(lib.gcl_adam_f32(self.flat_param.data_ptr(), self.flat_grad.data_ptr(),
-                                         self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.num_params,
+                                         self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.flat_size,
                                          self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world,
                                          self.step_count.data_ptr(), torch.cuda.current_stream().cuda_stream),
                         "gcl_adam_f32")

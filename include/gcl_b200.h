@@ -101,7 +101,7 @@ int gcl_csr_weights(const int32_t* rowptr, const int32_t* col, const int32_t* pe
 int gcl_spmm_f32(const int32_t* rowptr, const int32_t* col, const float* w, const float* x,
                  float* out, int64_t batch, int64_t n_rows_out, int64_t channels, int64_t x_bstride,
                  int64_t out_bstride, const float* bias, const float* prelu_slope, float* z_out,
-                 void* stream);
+                 int64_t nnz /* number of CSR entries, 0 = unknown (scheduling hint only) */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K7  node-wise dense transform  y = act(x W^T + b)  (torch.nn.Linear in MLP, models.py:74-98, and the
@@ -140,6 +140,13 @@ int gcl_prelu_fwd_f32(const float* x, const float* slope, float* y, int64_t n, v
 size_t gcl_prelu_bwd_workspace_bytes(int64_t n);
 int gcl_prelu_bwd_f32(const float* dy, const float* x, const float* slope, float* dx, float* dslope,
                       int64_t n, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same, fused with the column sums of dx: dbias[C] = sum_rows dx (the bias gradient of the conv whose
+ * output fed this PReLU; models.py:323-328 alternates GCNConv and the shared PReLU).  dy, x, dx [R, C]. */
+size_t gcl_prelu_bwd_colsum_workspace_bytes(int64_t rows, int64_t c);
+int gcl_prelu_bwd_colsum_f32(const float* dy, const float* x, const float* slope, float* dx,
+                             float* dslope, float* dbias, int64_t rows, int64_t c, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a6  torch_geometric.nn.LayerNorm (models.py:103,370).

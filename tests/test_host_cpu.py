@@ -106,7 +106,8 @@ def _dp_worker(rank, world, port, out):
         dist.all_gather(gl, local)
         ok_sum = torch.allclose(tr.flat_grad, sum(gl), rtol=0, atol=1e-7)
         views = all(p.data_ptr() >= tr.flat_param.data_ptr() and
-                    p.data_ptr() < tr.flat_param.data_ptr() + 4 * tr.num_params for p in model.parameters())
+                    p.data_ptr() < tr.flat_param.data_ptr() + 4 * tr.flat_size and p.data_ptr() % 128 == tr.flat_param.data_ptr() % 128
+                    for p in model.parameters())
         out[rank] = (same_weights, ok_sum, views, tr.world, tr.num_params)
     finally:
         dist.destroy_process_group()

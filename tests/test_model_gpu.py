@@ -105,7 +105,10 @@ def _check_grads(mine, ref, tol, what):
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, f"{what}: unexpected grad for {k}"
             continue
         assert p.grad is not None, f"{what}: missing grad for {k}"
-        assert_close(p.grad, pr[k].grad, tol, f"{what} d{k}", atol=1e-9)
+        # d att_dst is analytically ~0 (softmax is invariant to a per-receiver shift, only LeakyReLU breaks
+        # it), i.e. a cancelling sum: judge it on an absolute floor relative to d att_src
+        extra = 1e-4 * float(pr[k.replace("att_dst", "att_src")].grad.abs().max()) if k.endswith("att_dst") else 0.0
+        assert_close(p.grad, pr[k].grad, tol, f"{what} d{k}", atol=max(1e-9, extra))
         n += 1
     assert n > 0
 
@@ -200,7 +203,8 @@ def test_against_unmodified_reference_fixture(name, golden_dir):
     assert abs(float(loss) - float(z["loss"])) <= RTOL_F32 * abs(float(z["loss"]))
     for k, p in m.named_parameters():
         if "grad/" + k in z.files:
-            assert_close(p.grad, torch.from_numpy(z["grad/" + k]), RTOL_F32, f"d{k}")
+            extra = 1e-4 * float(np.abs(z["grad/" + k.replace("att_dst", "att_src")]).max()) if k.endswith("att_dst") else 0.0
+            assert_close(p.grad, torch.from_numpy(z["grad/" + k]), RTOL_F32, f"d{k}", atol=extra)
     if name == "sparse_attention":
         with torch.no_grad():
             m(X=X, attention_threshold=0.05, batch_num=0)
