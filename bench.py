@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--kernel-rows", type=int, default=12, help="rows of the per-kernel table kept in the JSON line")
     return ap.parse_args()
 
 
@@ -266,7 +267,7 @@ def run_gcl(args):
         ops.PROFILER = None
         total = sum(a["ms"] for a in agg.values()) or 1.0
         rows = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
-        for (name, tag), a in rows[:12]:
+        for (name, tag), a in rows[:args.kernel_rows]:
             gbs = a["bytes"] / (a["ms"] * 1e-3) / 1e9 if a["ms"] > 0 else 0.0
             by_kernel.append({"kernel": name, "shape": tag, "calls_per_step": a["calls"] / args.profile_steps,
                               "us_per_call": 1e3 * a["ms"] / a["calls"], "share": a["ms"] / total,

@@ -14,9 +14,16 @@
 // warp may only touch TMEM lanes 32*(warp%4)..+31), warp 4 allocates TMEM and its lane 0 issues the
 // MMAs, warps 5-11 load/split/stage.  mbarrier rings: full/empty per smem stage, full/empty per TMEM
 // accumulator (two accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1).
+#include <cuda.h>   // CUtensorMap types only; the encoder is resolved at run time
+
 #include "common.cuh"
 
 namespace gcl {
+// debugging / A-B switch (GCL_UMMA_NO_TMA=1): keep the register-staged kernels even where TMA applies
+static const bool g_force_register_staging = [] {
+  const char* e = getenv("GCL_UMMA_NO_TMA");
+  return e && e[0] == '1';
+}();
 namespace {
 
 constexpr int kTileM = 128;
@@ -84,6 +91,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two 16-column loads in flight, one wait; the wait takes the destination registers as in/out operands so no
+// consumer can be scheduled above it
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr_a, uint32_t taddr_b, float (&a)[16], float (&b)[16]) {
+  uint32_t r[16], q[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr_a));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(taddr_b));
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]),
+                 "+r"(q[8]), "+r"(q[9]), "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15])
+               :
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    a[i] = __uint_as_float(r[i]);
+    b[i] = __uint_as_float(q[i]);
+  }
+}
+
 __device__ __forceinline__ bool al16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // one contiguous, 16 B aligned chunk smem -> global through the bulk-copy (TMA) engine
@@ -122,6 +157,42 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
 }
+// The MMA-issuing warp is a single instruction stream, and ncu showed it -- not DRAM, not the tensor core --
+// pacing the kernels when every MMA rebuilt its descriptors and ring indices with divisions.  So: the K-major
+// SWIZZLE_128B descriptor is split into a constant high word and a low word (address >> 4 | LBO) that advances
+// by 2 per 8-element K step, ring positions are counters, and the loop runs warp-uniform with one elected lane.
+constexpr uint32_t kDescHiK128 = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));   // SBO=1024, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_k128(uint32_t lo) { return ((uint64_t)kDescHiK128 << 32) | lo; }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+// the three 3xTF32 products of one 8-element K step (small terms first)
+__device__ __forceinline__ void umma_3x(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                        uint32_t idesc, uint32_t accumulate) {
+  umma_tf32(d_tmem, desc_k128(a_lo), desc_k128(b_hi), idesc, accumulate);
+  umma_tf32(d_tmem, desc_k128(a_hi), desc_k128(b_lo), idesc, 1u);
+  umma_tf32(d_tmem, desc_k128(a_hi), desc_k128(b_hi), idesc, 1u);
+}
+
+// Same products, but the two correction terms go to their own accumulator.  The tensor core adds into its fp32
+// accumulator with truncation (measured: positive operands come out ~5e-7 low after the 24 accumulation steps
+// of a K = 64 row); keeping the ~2^-11-sized corrections out of the main accumulator leaves it 8 steps, and
+// the epilogue adds the two with an ordinary rounded fp32 add.
+__device__ __forceinline__ void umma_3x_split(uint32_t d_main, uint32_t d_corr, uint32_t a_hi, uint32_t a_lo,
+                                              uint32_t b_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  umma_tf32(d_corr, desc_k128(a_lo), desc_k128(b_hi), idesc, accumulate);
+  umma_tf32(d_corr, desc_k128(a_hi), desc_k128(b_lo), idesc, 1u);
+  umma_tf32(d_main, desc_k128(a_hi), desc_k128(b_hi), idesc, accumulate);
+}
+
 // cute::UMMA::InstrDescriptor: D = F32, A = B = TF32, M = 128, N; major bits 0 = K-major, 1 = MN-major
 __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -259,34 +330,33 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == kEpiWarps) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(n_pad, 0, 0);
-      int64_t it_local = 0, t_local = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_local) {
-        const int acc = (int)(t_local & 1);
-        mbar_wait(bars + 8 * (2 * nst + 2 + acc), (uint32_t)(((t_local >> 1) & 1) ^ 1));   // accumulator drained
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    const uint32_t idesc = make_idesc(n_pad, 0, 0);
+    const uint32_t a_lo0 = desc_lo(smem_u32(a_st)), bh_lo = desc_lo(smem_u32(b_hi)), bl_lo = desc_lo(smem_u32(b_lo));
+    const uint32_t b_step = (uint32_t)b_block >> 4;
+    int st = 0;
+    uint32_t ph = 0;
+    int64_t t_local = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_local) {
+      const int acc = (int)(t_local & 1);
+      mbar_wait(bars + 8 * (2 * nst + 2 + acc), (uint32_t)(((t_local >> 1) & 1) ^ 1));   // accumulator drained
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * n_pad);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(bars + 8 * st, ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * n_pad);
-        for (int kb = 0; kb < nkb; ++kb, ++it_local) {
-          const int st = (int)(it_local % nst);
-          mbar_wait(bars + 8 * st, (uint32_t)((it_local / nst) & 1));
-          tc_fence_after();
-          const uint32_t a_hi = smem_u32(a_st + (size_t)st * 2 * kPartBytes);
-          const uint32_t a_lo = a_hi + kPartBytes;
-          const uint32_t bh = smem_u32(b_hi + (size_t)kb * b_block);
-          const uint32_t bl = smem_u32(b_lo + (size_t)kb * b_block);
+        if (elect_one()) {
+          const uint32_t ah = a_lo0 + (uint32_t)st * (2 * kPartBytes >> 4), al = ah + (kPartBytes >> 4);
+          const uint32_t bh = bh_lo + (uint32_t)kb * b_step, bl = bl_lo + (uint32_t)kb * b_step;
           const int ksteps = min(4, (K - kb * kKB + 7) / 8);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t da_hi = make_desc(a_hi + ks * 32, 16, 1024), da_lo = make_desc(a_lo + ks * 32, 16, 1024);
-            const uint64_t db_hi = make_desc(bh + ks * 32, 16, 1024), db_lo = make_desc(bl + ks * 32, 16, 1024);
-            umma_tf32(d_tmem, da_lo, db_hi, idesc, (kb | ks) ? 1u : 0u);   // small terms first
-            umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
-            umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
-          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            if (ks < ksteps) umma_3x(d_tmem, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
           umma_commit(bars + 8 * (nst + st));                // smem stage free once these MMAs retire
+          if (kb == nkb - 1) umma_commit(bars + 8 * (2 * nst + acc));   // accumulator complete -> epilogue
         }
-        umma_commit(bars + 8 * (2 * nst + acc));             // accumulator complete -> epilogue
+        __syncwarp();
+        if (++st == nst) { st = 0; ph ^= 1; }
       }
     }
   } else {
@@ -527,27 +597,24 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == kEpiWarps) {
-    if (lane == 0 && nkb > 0) {
-      const uint32_t idesc = make_idesc(n_pad, 0, 0);
-      for (int64_t kb = 0; kb < nkb; ++kb) {
-        const int st = (int)(kb % nst);
-        mbar_wait(bars + 8 * st, (uint32_t)((kb / nst) & 1));
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(st_base + (size_t)st * stage_bytes);
-        const uint32_t a_lo = a_hi + kPartBytes;
-        const uint32_t b_hi = a_lo + kPartBytes;
-        const uint32_t b_lo = b_hi + b_part;
+    const uint32_t idesc = make_idesc(n_pad, 0, 0);
+    const uint32_t st_lo = desc_lo(smem_u32(st_base));
+    int st = 0;
+    uint32_t ph = 0;
+    for (int64_t kb = 0; kb < nkb; ++kb) {
+      mbar_wait(bars + 8 * st, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t ah = st_lo + (uint32_t)st * ((uint32_t)stage_bytes >> 4), al = ah + (kPartBytes >> 4);
+        const uint32_t bh = al + (kPartBytes >> 4), bl = bh + ((uint32_t)b_part >> 4);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t da_hi = make_desc(a_hi + ks * 32, 16, 1024), da_lo = make_desc(a_lo + ks * 32, 16, 1024);
-          const uint64_t db_hi = make_desc(b_hi + ks * 32, 16, 1024), db_lo = make_desc(b_lo + ks * 32, 16, 1024);
-          umma_tf32(tmem_base, da_lo, db_hi, idesc, (kb | ks) ? 1u : 0u);
-          umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
-          umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
-        }
+        for (int ks = 0; ks < 4; ++ks)
+          umma_3x(tmem_base, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
         umma_commit(bars + 8 * (nst + st));
+        if (kb == nkb - 1) umma_commit(bars + 8 * (2 * nst));
       }
-      umma_commit(bars + 8 * (2 * nst));
+      __syncwarp();
+      if (++st == nst) { st = 0; ph ^= 1; }
     }
   } else {
     const int m = warp * 32 + lane;
@@ -571,6 +638,417 @@ __global__ void __launch_bounds__(kThreads, 1)
     } else if (m < M) {
       for (int n = 0; n < N; ++n) prow[n] = 0.f;
       if (part_colsum) part_colsum[(int64_t)blockIdx.x * M + m] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-fed variant of the linear kernel (the default whenever rows are 16-byte aligned).
+//
+// The register-staged kernel above moves every byte through the LSU twice and leaves the tile as 128
+// separate 256-byte bulk copies (UBLKCP is issued per lane, serially): ncu showed neither DRAM nor the tensor
+// core busy, just long-scoreboard and bulk-copy issue stalls at ~3.4 TB/s.  Here the copy engine does the
+// moving, in 16 KB boxes:
+//   * TMA loads [128 rows x 32 floats] slabs of A straight into the K-major SWIZZLE_128B layout.  The raw
+//     fp32 slab IS the hi operand: kind::tf32 reads the top 19 bits of each word, i.e. hi = trunc_tf32(x);
+//   * six converter warps compute lo = x - trunc_tf32(x) (exact) smem -> smem at the same swizzled offset,
+//     one LDS.128 + one STS.128 per four elements, conflict-free;
+//   * the epilogue writes the output tile into SWIZZLE_128B slabs (conflict-free by construction) and one
+//     thread sends it with one TMA tensor store per 32-column slab; row / column tails are clipped by the
+//     tensor map, so there is no tail code at all.
+// hi by truncation biases the dropped lo(A) lo(W) term (<= 2^-21 relative per product, see split_tf32);
+// W keeps the rounded split.
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float lo_trunc(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+constexpr int kSlabBytes = kTileM * 128;     // [128 rows x 32 fp32], 16 KB
+constexpr int kConvWarps = 6;                // warps 6..11
+constexpr int kConvThreads = kConvWarps * 32;
+constexpr int kDwConvWarps = kConvWarps + kEpiWarps;   // dW: the epilogue warps convert too until the last MMA
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32x4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// roles (14 warps): 0-7 epilogue (warp w owns TMEM lanes 32 (w % 4).. and the 16-column blocks with
+// block % 2 == w / 4), 8 MMA issue + TMEM allocation, 9 TMA producer, 10-13 converters
+constexpr int kLtEpiWarps = 8, kLtConvWarps = 4;
+constexpr int kLtMmaWarp = kLtEpiWarps, kLtTmaWarp = kLtEpiWarps + 1;
+constexpr int kLtThreads = (kLtEpiWarps + 2 + kLtConvWarps) * 32;      // 448
+constexpr int kLtConvThreads = kLtConvWarps * 32, kLtEpiThreads = kLtEpiWarps * 32;
+
+__global__ void __launch_bounds__(kLtThreads, 1)
+    umma_linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
+                           const __grid_constant__ CUtensorMap tmZ, const float* __restrict__ W, int64_t M, int N,
+                           int K, int n_pad, int nkb, int nob, int s_raw, int s_lo, int nbuf, int tmem_cols, int has_z,
+                           const float* __restrict__ bias, const float* __restrict__ prelu_slope) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_block = n_pad * 128;
+  uint8_t* b_hi = smem;
+  uint8_t* b_lo = b_hi + (size_t)nkb * b_block;
+  uint8_t* raw = b_lo + (size_t)nkb * b_block;
+  uint8_t* lo = raw + (size_t)s_raw * kSlabBytes;
+  uint8_t* c_out = lo + (size_t)s_lo * kSlabBytes;                     // [nbuf][1 + has_z][nob] slabs
+  const int out_buf_bytes = (1 + has_z) * nob * kSlabBytes;
+  float* bias_s = reinterpret_cast<float*>(c_out + (size_t)nbuf * out_buf_bytes);
+  uint64_t* bar_ptr = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bias_s + n_pad) + 15) & ~uintptr_t(15));
+  const uint32_t bars = smem_u32(bar_ptr);
+  const int kRawFull = 0, kRawEmpty = s_raw, kLoFull = 2 * s_raw, kLoEmpty = 2 * s_raw + s_lo,
+            kAccFull = 2 * s_raw + 2 * s_lo, kAccEmpty = kAccFull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + kAccEmpty + 2);
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (M + kTileM - 1) / kTileM;
+  const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_items = my_tiles * nkb;
+
+  if (tid == 0) {
+    for (int s = 0; s < s_raw; ++s) {
+      mbar_init(bar(kRawFull + s), 1);
+      mbar_init(bar(kRawEmpty + s), 1);
+    }
+    for (int s = 0; s < s_lo; ++s) {
+      mbar_init(bar(kLoFull + s), kLtConvThreads);
+      mbar_init(bar(kLoEmpty + s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar(kAccFull + a), 1);
+      mbar_init(bar(kAccEmpty + a), kLtEpiThreads);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kLtMmaWarp) tmem_alloc(smem_u32(tmem_slot), (uint32_t)tmem_cols);
+  for (int idx = tid; idx < nkb * n_pad * 8; idx += kLtThreads) {       // W -> rounded hi/lo, resident
+    const int c = idx & 7, n = (idx >> 3) % n_pad, kb = (idx >> 3) / n_pad;
+    const int k = kb * kKB + c * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N && k < K) v = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * K + k));
+    split_store(b_hi + (size_t)kb * b_block, b_lo + (size_t)kb * b_block, sw_off(n, c), v);
+  }
+  for (int n = tid; n < n_pad; n += kLtThreads) bias_s[n] = (bias && n < N) ? __ldg(bias + n) : 0.f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kLtTmaWarp) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(bar(kRawEmpty + s), ph);
+          mbar_expect_tx(bar(kRawFull + s), kSlabBytes);
+          tma_load_2d(smem_u32(raw + (size_t)s * kSlabBytes), &tmA, kb * kKB, (int)(tile * kTileM), bar(kRawFull + s));
+          if (++s == s_raw) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp > kLtTmaWarp) {
+    // ===================== converters: lo = x - trunc_tf32(x), same swizzled offset =====================
+    const int ct = tid - (kLtTmaWarp + 1) * 32;          // 0..127
+    int s = 0, l = 0;
+    uint32_t sph = 0, lph = 1;
+    for (int64_t it = 0; it < my_items; ++it) {
+      mbar_wait(bar(kRawFull + s), sph);
+      mbar_wait(bar(kLoEmpty + l), lph);
+      const float4* src = reinterpret_cast<const float4*>(raw + (size_t)s * kSlabBytes);
+      float4* dst = reinterpret_cast<float4*>(lo + (size_t)l * kSlabBytes);
+#pragma unroll
+      for (int i = 0; i < 1024 / kLtConvThreads; ++i) {
+        const float4 v = src[ct + i * kLtConvThreads];
+        dst[ct + i * kLtConvThreads] = make_float4(lo_trunc(v.x), lo_trunc(v.y), lo_trunc(v.z), lo_trunc(v.w));
+      }
+      fence_proxy_async();
+      mbar_arrive(bar(kLoFull + l));
+      if (++s == s_raw) { s = 0; sph ^= 1; }
+      if (++l == s_lo) { l = 0; lph ^= 1; }
+    }
+  } else if (warp == kLtMmaWarp) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    const uint32_t idesc = make_idesc(n_pad, 0, 0);
+    const uint32_t raw_lo = desc_lo(smem_u32(raw)), lo_lo = desc_lo(smem_u32(lo));
+    const uint32_t bh_lo = desc_lo(smem_u32(b_hi)), bl_lo = desc_lo(smem_u32(b_lo));
+    const uint32_t b_step = (uint32_t)b_block >> 4;
+    int rs = 0, ls = 0;
+    uint32_t rph = 0, lph = 0;
+    int64_t t_local = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_local) {
+      const int acc = (int)(t_local & 1);
+      mbar_wait(bar(kAccEmpty + acc), (uint32_t)(((t_local >> 1) & 1) ^ 1));
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * n_pad), d_corr = d_tmem + (uint32_t)n_pad;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(bar(kRawFull + rs), rph);
+        mbar_wait(bar(kLoFull + ls), lph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t ah = raw_lo + (uint32_t)rs * (kSlabBytes >> 4), al = lo_lo + (uint32_t)ls * (kSlabBytes >> 4);
+          const uint32_t bh = bh_lo + (uint32_t)kb * b_step, bl = bl_lo + (uint32_t)kb * b_step;
+          const int ksteps = min(4, (K - kb * kKB + 7) / 8);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            if (ks < ksteps)
+              umma_3x_split(d_tmem, d_corr, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+          umma_commit(bar(kRawEmpty + rs));
+          umma_commit(bar(kLoEmpty + ls));
+          if (kb == nkb - 1) umma_commit(bar(kAccFull + acc));
+        }
+        __syncwarp();
+        if (++rs == s_raw) { rs = 0; rph ^= 1; }
+        if (++ls == s_lo) { ls = 0; lph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> swizzled smem slabs -> TMA tensor store ========
+    // With two output buffers the only synchronisation per tile is one named barrier: thread 0 waits (before
+    // it) until the PREVIOUS tile's stores have finished reading their buffer, which is the one the NEXT tile
+    // writes.  With one buffer (not enough smem for two) that wait has to sit in front of the writes.
+    const float slope = prelu_slope ? __ldg(prelu_slope) : 0.f;
+    const int my = (warp & 3) * 32 + lane, cgrp = warp >> 2;
+    int64_t t_local = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_local) {
+      const int acc = (int)(t_local & 1);
+      uint8_t* ob = c_out + (size_t)(nbuf == 2 ? (t_local & 1) : 0) * out_buf_bytes;
+      uint8_t* zb = ob + (size_t)nob * kSlabBytes;
+      if (nbuf == 1 && t_local > 0) {
+        if (tid == 0) bulk_wait_read();
+        named_bar(1, kLtEpiThreads);
+      }
+      mbar_wait(bar(kAccFull + acc), (uint32_t)((t_local >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * 2 * n_pad);
+      for (int c0 = cgrp * 16; c0 < n_pad; c0 += 32) {
+        float v[16], vc[16];
+        tmem_ld16x2(taddr + c0, taddr + n_pad + c0, v, vc);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col = c0 + 4 * q;
+          const uint32_t off = (uint32_t)(col >> 5) * kSlabBytes + sw_off(my, (col & 31) >> 2);
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col);
+          float4 o = make_float4((v[4 * q] + vc[4 * q]) + b4.x, (v[4 * q + 1] + vc[4 * q + 1]) + b4.y,
+                                 (v[4 * q + 2] + vc[4 * q + 2]) + b4.z, (v[4 * q + 3] + vc[4 * q + 3]) + b4.w);
+          if (has_z) *reinterpret_cast<float4*>(zb + off) = o;
+          if (prelu_slope)
+            o = make_float4(prelu_f(o.x, slope), prelu_f(o.y, slope), prelu_f(o.z, slope), prelu_f(o.w, slope));
+          *reinterpret_cast<float4*>(ob + off) = o;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar(kAccEmpty + acc));
+      fence_proxy_async();
+      if (nbuf == 2 && tid == 0) bulk_wait_read();
+      named_bar(1, kLtEpiThreads);
+      if (tid == 0) {
+        for (int j = 0; j < nob; ++j) {
+          tma_store_2d(&tmC, j * kKB, (int)(tile * kTileM), smem_u32(ob + (size_t)j * kSlabBytes));
+          if (has_z) tma_store_2d(&tmZ, j * kKB, (int)(tile * kTileM), smem_u32(zb + (size_t)j * kSlabBytes));
+        }
+        bulk_commit();
+      }
+    }
+    if (tid == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kLtMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-fed dW: the copy engine brings [32 rows x M] / [32 rows x N] boxes of dY / X (row-major, unswizzled)
+// into a raw ring, the converter warps transpose + split them smem -> smem into the K-major stages (a lane
+// owns one column and four consecutive rows = one 16-byte K chunk, both sides conflict-free), so no global
+// load latency sits on any warp's critical path.  Row tails are zero-filled by the tensor map.
+__global__ void __launch_bounds__(kThreads, 1)
+    umma_dw_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       float* __restrict__ part, float* __restrict__ part_colsum, int64_t R, int M, int N, int n_pad,
+                       int nst, int nraw, int raw_bytes, int tmem_cols, int64_t rows_per_cta) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_part = n_pad * 128;
+  const int stage_bytes = 2 * kPartBytes + 2 * b_part;
+  uint8_t* st_base = smem;
+  uint8_t* raw = st_base + (size_t)nst * stage_bytes;
+  uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(raw + (size_t)nraw * raw_bytes);
+  const uint32_t bars = smem_u32(bar_ptr);
+  const int kFull = 0, kEmpty = nst, kRawFull = 2 * nst, kRawEmpty = 2 * nst + nraw, kAccFull = 2 * nst + 2 * nraw;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + kAccFull + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t r_beg = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = min(R, r_beg + rows_per_cta);
+  const int64_t nkb = r_end > r_beg ? (r_end - r_beg + kKB - 1) / kKB : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < nst; ++s) {
+      mbar_init(bar(kFull + s), kDwConvWarps * 32);
+      mbar_init(bar(kEmpty + s), 1);
+    }
+    for (int s = 0; s < nraw; ++s) {
+      mbar_init(bar(kRawFull + s), 1);
+      mbar_init(bar(kRawEmpty + s), kDwConvWarps * 32);
+    }
+    mbar_init(bar(kAccFull), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kEpiWarps) tmem_alloc(smem_u32(tmem_slot), (uint32_t)tmem_cols);
+  for (int i = tid; i < nst * stage_bytes / 16; i += kThreads)
+    reinterpret_cast<float4*>(st_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (int i = tid; i < nst * 8; i += kThreads) {
+    uint8_t* b_hi = st_base + (size_t)(i >> 3) * stage_bytes + 2 * kPartBytes;
+    *reinterpret_cast<float4*>(b_hi + sw_off(N, i & 7)) = make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kEpiWarps + 1) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int64_t kb = 0; kb < nkb; ++kb) {
+        const int row = (int)(r_beg + kb * kKB);
+        mbar_wait(bar(kRawEmpty + s), ph);
+        mbar_expect_tx(bar(kRawFull + s), (uint32_t)(kKB * (M + N) * 4));
+        const uint32_t dst = smem_u32(raw + (size_t)s * raw_bytes);
+        tma_load_2d(dst, &tmA, 0, row, bar(kRawFull + s));
+        tma_load_2d(dst + (uint32_t)(kKB * M * 4), &tmB, 0, row, bar(kRawFull + s));
+        if (++s == nraw) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp != kEpiWarps) {
+    // converters: warps 0-3 (which run the epilogue afterwards) and 6-11
+    const int cw = warp < kEpiWarps ? warp : warp - 2;     // 0..9
+    const int na_units = 8 * ((M + 31) / 32), n_units = na_units + 8 * ((N + 31) / 32);
+    const uint32_t st_u32 = smem_u32(st_base), raw_u32 = smem_u32(raw);
+    int st = 0, rs = 0;
+    uint32_t ph = 1, rph = 0;
+    constexpr int kBatch = 4;                              // units in flight per warp (16 LDS.32)
+    for (int64_t kb = 0; kb < nkb; ++kb) {
+      mbar_wait(bar(kRawFull + rs), rph);
+      mbar_wait(bar(kEmpty + st), ph);
+      const uint32_t ra = raw_u32 + (uint32_t)rs * (uint32_t)raw_bytes, rb = ra + (uint32_t)(kKB * M * 4);
+      const uint32_t a_hi = st_u32 + (uint32_t)st * (uint32_t)stage_bytes;
+      const uint32_t b_hi = a_hi + 2 * kPartBytes;
+      for (int u0 = cw; u0 < n_units; u0 += kBatch * kDwConvWarps) {
+        float4 v[kBatch];
+        uint32_t dst[kBatch];
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+          const int u = u0 + i * kDwConvWarps;
+          const bool isa = u < na_units;
+          const int uu = isa ? u : u - na_units;
+          const int width = isa ? M : N;
+          const int col = (uu >> 3) * 32 + lane, chunk = uu & 7;
+          dst[i] = 0xffffffffu;
+          if (u < n_units && col < width) {
+            const uint32_t src = (isa ? ra : rb) + (uint32_t)(((chunk * 4) * width + col) * 4);
+            const uint32_t w4 = (uint32_t)width * 4;
+            v[i] = make_float4(lds_f32(src), lds_f32(src + w4), lds_f32(src + 2 * w4), lds_f32(src + 3 * w4));
+            dst[i] = (isa ? a_hi : b_hi) + sw_off(col, chunk);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+          if (dst[i] != 0xffffffffu) {
+            const int u = u0 + i * kDwConvWarps;
+            float4 h, l;
+            split_tf32(v[i].x, h.x, l.x);
+            split_tf32(v[i].y, h.y, l.y);
+            split_tf32(v[i].z, h.z, l.z);
+            split_tf32(v[i].w, h.w, l.w);
+            sts_f32x4(dst[i], h);
+            sts_f32x4(dst[i] + (u < na_units ? (uint32_t)kPartBytes : (uint32_t)b_part), l);
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bar(kFull + st));
+      mbar_arrive(bar(kRawEmpty + rs));
+      if (++st == nst) { st = 0; ph ^= 1; }
+      if (++rs == nraw) { rs = 0; rph ^= 1; }
+    }
+    if (warp < kEpiWarps) {
+      // ---- epilogue: the accumulator is complete once the last MMA has retired
+      const int m = warp * 32 + lane;
+      float* prow = part + ((int64_t)blockIdx.x * M + m) * N;
+      if (nkb > 0) {
+        mbar_wait(bar(kAccFull), 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < n_pad; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          if (m < M) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = c0 + j;
+              if (n < N) prow[n] = v[j];
+              else if (n == N && part_colsum) part_colsum[(int64_t)blockIdx.x * M + m] = v[j];
+            }
+          }
+        }
+      } else if (m < M) {
+        for (int n = 0; n < N; ++n) prow[n] = 0.f;
+        if (part_colsum) part_colsum[(int64_t)blockIdx.x * M + m] = 0.f;
+      }
+    }
+  } else if (warp == kEpiWarps) {
+    const uint32_t idesc = make_idesc(n_pad, 0, 0);
+    const uint32_t st_lo = desc_lo(smem_u32(st_base));
+    int st = 0;
+    uint32_t ph = 0;
+    for (int64_t kb = 0; kb < nkb; ++kb) {
+      mbar_wait(bar(kFull + st), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t ah = st_lo + (uint32_t)st * ((uint32_t)stage_bytes >> 4), al = ah + (kPartBytes >> 4);
+        const uint32_t bh = al + (kPartBytes >> 4), bl = bh + ((uint32_t)b_part >> 4);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_3x(tmem_base, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+        umma_commit(bar(kEmpty + st));
+        if (kb == nkb - 1) umma_commit(bar(kAccFull));
+      }
+      __syncwarp();
+      if (++st == nst) { st = 0; ph ^= 1; }
     }
   }
   tc_fence_before();
@@ -630,10 +1108,101 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 }  // namespace
 
 
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// the driver's tensor-map encoder, resolved through the runtime (no link-time dependency on libcuda)
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// fp32 [rows, cols] row-major, boxes of [box_rows x box_cols]; out-of-range elements load as 0 / are not stored
+bool make_map_2d(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int box_rows, int box_cols,
+                 CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct TmaLinPlan {
+  int n_pad, nkb, nob, s_raw, s_lo, nbuf, tmem_cols;
+  size_t smem;
+  bool ok;
+};
+TmaLinPlan plan_linear_tma(int64_t N, int64_t K, bool has_z) {
+  TmaLinPlan p{};
+  p.n_pad = (int)((N + 15) / 16 * 16);
+  p.nkb = (int)((K + kKB - 1) / kKB);
+  p.nob = (int)((N + kKB - 1) / kKB);
+  if (N < kKB || K < kKB || p.n_pad > 256 || (N & 3) || (K & 3)) return p;
+  const long w_bytes = 2L * p.nkb * p.n_pad * 128;
+  const long fixed = 1024 + 512 + 4L * p.n_pad;
+  long slabs = 0, out_bytes = 0;
+  for (p.nbuf = 2; p.nbuf >= 1; --p.nbuf) {       // two output buffers if at least 7 operand slabs remain
+    out_bytes = (long)p.nbuf * p.nob * kSlabBytes * (has_z ? 2 : 1);
+    slabs = ((long)kMaxSmem - w_bytes - out_bytes - fixed) / kSlabBytes;
+    if (slabs >= (p.nbuf == 2 ? 7 : 5)) break;
+  }
+  if (p.nbuf < 1) return p;
+  p.s_lo = (int)(slabs * 2 / 5);
+  if (p.s_lo > 4) p.s_lo = 4;
+  p.s_raw = (int)(slabs - p.s_lo);
+  if (p.s_raw > 8) p.s_raw = 8;
+  p.smem = (size_t)(w_bytes + out_bytes + fixed + (long)(p.s_raw + p.s_lo) * kSlabBytes);
+  int cols = 32;
+  while (cols < 4 * p.n_pad) cols <<= 1;     // two tiles in flight x (main + correction accumulator)
+  if (cols > 512) return p;
+  p.tmem_cols = cols;
+  p.ok = true;
+  return p;
+}
+
+int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
+                    const float* slope, float* z_out, cudaStream_t s) {
+  if (!(al16(A) && al16(W_nk) && al16(C) && (!z_out || al16(z_out))) || M <= 0 || M > 0x7fffff00LL)
+    return GCL_ERR_UNSUPPORTED;
+  const TmaLinPlan p = plan_linear_tma(N, K, z_out != nullptr);
+  if (!p.ok) return GCL_ERR_UNSUPPORTED;
+  CUtensorMap tmA, tmC, tmZ;
+  if (!make_map_2d(&tmA, A, M, K, kTileM, kKB, CU_TENSOR_MAP_SWIZZLE_128B) ||
+      !make_map_2d(&tmC, C, M, N, kTileM, kKB, CU_TENSOR_MAP_SWIZZLE_128B) ||
+      !make_map_2d(&tmZ, z_out ? z_out : C, M, N, kTileM, kKB, CU_TENSOR_MAP_SWIZZLE_128B))
+    return GCL_ERR_UNSUPPORTED;
+  const int64_t ntiles = (M + kTileM - 1) / kTileM;
+  const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+  cudaError_t e =
+      cudaFuncSetAttribute(umma_linear_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  if (e != cudaSuccess) return fail_cuda(e, "umma_linear_tma(smem attr)");
+  umma_linear_tma_kernel<<<grid, kLtThreads, p.smem, s>>>(tmA, tmC, tmZ, W_nk, M, (int)N, (int)K, p.n_pad, p.nkb,
+                                                          p.nob, p.s_raw, p.s_lo, p.nbuf, p.tmem_cols, z_out ? 1 : 0,
+                                                          bias, slope);
+  GCL_CHECK_LAUNCH("umma_linear_tma");
+  return GCL_OK;
+}
+}  // namespace
+
 // Returns GCL_OK when launched, GCL_ERR_UNSUPPORTED when the shape does not fit (caller falls back to
 // the FFMA kernel), or an error.
 int umma_linear(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
                 const float* slope, float* z_out, cudaStream_t s) {
+  if (!g_force_register_staging) {
+    const int rc = umma_linear_tma(A, W_nk, C, M, N, K, bias, slope, z_out, s);
+    if (rc != GCL_ERR_UNSUPPORTED) return rc;
+  }
   LinPlan p = plan_linear(N, K, z_out != nullptr, al16(C) && (!z_out || al16(z_out)));
   if (!p.ok || M <= 0) return GCL_ERR_UNSUPPORTED;
   const bool vec = (K % 4 == 0) && al16(A) && al16(W_nk);
@@ -695,6 +1264,30 @@ int umma_dw(const float* A, const float* B, float* part, float* part_colsum, int
             cudaStream_t s) {
   DwUmmaPlan p = plan_dw(R, M, N);
   if (!p.ok) return GCL_ERR_UNSUPPORTED;
+  if (!g_force_register_staging && (M & 3) == 0 && (N & 3) == 0 && al16(A) && al16(B) && R <= 0x7fffff00LL) {
+    // raw ring + as many K-major stages as fit
+    const int raw_bytes = (int)((kKB * (M + N) * 4 + 127) / 128 * 128);
+    const size_t stage = 2 * (size_t)kPartBytes + 2 * (size_t)p.n_pad * 128;
+    const size_t fixed = 1024 + 512;
+    int nst = 3, nraw = 0;
+    for (; nst >= 2; --nst) {
+      const long room = (long)kMaxSmem - (long)fixed - (long)nst * (long)stage;
+      nraw = room > 0 ? (int)(room / raw_bytes) : 0;
+      if (nraw >= 3 || (nst == 2 && nraw >= 2)) break;
+    }
+    if (nraw > 8) nraw = 8;
+    CUtensorMap tmA, tmB;
+    if (nst >= 2 && nraw >= 2 && make_map_2d(&tmA, A, R, M, kKB, (int)M, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+        make_map_2d(&tmB, B, R, N, kKB, (int)N, CU_TENSOR_MAP_SWIZZLE_NONE)) {
+      const size_t smem = fixed + (size_t)nst * stage + (size_t)nraw * raw_bytes;
+      cudaError_t e = cudaFuncSetAttribute(umma_dw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail_cuda(e, "umma_dw_tma(smem attr)");
+      umma_dw_tma_kernel<<<p.grid, kThreads, smem, s>>>(tmA, tmB, part, part_colsum, R, (int)M, (int)N, p.n_pad, nst, nraw,
+                                                        raw_bytes, p.tmem_cols, p.rows_per_cta);
+      GCL_CHECK_LAUNCH("umma_dw_tma");
+      return GCL_OK;
+    }
+  }
   auto go = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return fail_cuda(e, "umma_dw(smem attr)");
