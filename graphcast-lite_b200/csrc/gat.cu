@@ -251,18 +251,46 @@ __global__ void __launch_bounds__(kWarps * 32, 3)
   }
 }
 
+// Butterfly transpose-reduce: every lane of an L-lane group holds L partial values p[0..L); afterwards lane g
+// holds the sum over the group's lanes of p[g].  L - 1 shuffles for L reductions (a shuffle tree per value would
+// be L log2 L).
+template <int L>
+__device__ __forceinline__ float xreduce(float (&p)[L], int gl, unsigned mask) {
+#pragma unroll
+  for (int o = L / 2; o >= 1; o >>= 1) {
+    const bool up = (gl & o) != 0;
+#pragma unroll
+    for (int m = 0; m < o; ++m) {
+      const float send = up ? p[m] : p[m + o];
+      const float keep = up ? p[m + o] : p[m];
+      p[m] = keep + __shfl_xor_sync(mask, send, o, L);
+    }
+  }
+  return p[0];
+}
+// sum over the lanes of a group that share gl % SB (strides SB, 2 SB, ..., L / 2)
+template <int L, int SB>
+__device__ __forceinline__ float gsum_strided(float v, unsigned mask) {
+#pragma unroll
+  for (int o = SB; o < L; o <<= 1) v += __shfl_xor_sync(mask, v, o, L);
+  return v;
+}
+
 // Backward pass 1, group per (receiver i, SB samples):
 //   dalpha_k = <do_h(i), z[col_k, h]>;  t = sum_k alpha_k dalpha_k;  g_k = alpha_k (dalpha_k - t) * LeakyReLU'
 //   g_csr[b,k,h] = g_k;  da_dst[b,i,h] = sum_k g_k
+// The row is walked in batches of NB = L / SB neighbours: the L partial dot products (NB neighbours x SB
+// samples) of a batch are transpose-reduced at once, which leaves lane l with the finished dalpha of
+// (neighbour l / SB, sample l % SB); everything after that is per-lane scalar work on its own (edge, sample).
 template <int VW, int L, int SB>
-__global__ void __launch_bounds__(kWarps * 32, 3)
+__global__ void __launch_bounds__(kWarps * 32, 2)
     gat_bwd_dst_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const float* __restrict__ z, const float* __restrict__ a_src,
                        const float* __restrict__ a_dst, const float* __restrict__ alpha_csr,
                        const float* __restrict__ dout, float* __restrict__ g_csr, float* __restrict__ da_dst,
                        int64_t N, int64_t nnz, int B, int H, int C, int concat, float slope) {
   using V = W<VW>;
-  constexpr int kGroups = 32 / L;
+  constexpr int kGroups = 32 / L, NB = L / SB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gl = lane & (L - 1);
   const unsigned mask = group_mask<L>(lane);
@@ -274,82 +302,108 @@ __global__ void __launch_bounds__(kWarps * 32, 3)
   const int HC = H * C, Cout = concat ? HC : C;
   const int words = (C + VW - 1) / VW, nchunks = (words + L - 1) / L;
   const float hs = concat ? 1.f : 1.f / (float)H;
-  const bool single = (end - beg) <= L;    // the whole row fits one pass: dalpha stays in registers
+  const bool single = (end - beg) <= L;    // at most SB batches: dalpha stays in registers
+  const bool one = nchunks == 1;           // the usual case: this lane's slice of do(i) is loaded once per head
+  const int jj = gl / SB, s_me = gl % SB;  // after the transpose-reduce this lane owns (neighbour jj, sample s_me)
+  const bool s_ok = s_me < nb;
+  const int64_t bs = b0 + s_me;
 
   for (int h = 0; h < H; ++h) {
-    float keep[SB], t[SB];
+    const float* dbase = dout + (concat ? h * C : 0);
+    typename V::T dv[SB];
 #pragma unroll
-    for (int s = 0; s < SB; ++s) keep[s] = t[s] = 0.f;
-    for (int32_t base = beg; base < end; base += L) {
-      const int n = min(L, end - base);
-      const int32_t k = base + gl;
-      const int32_t c_reg = (k < end) ? col[k] : 0;
-      float mine[SB];
+    for (int s = 0; s < SB; ++s)
+      dv[s] = (one && s < nb && gl * VW < C) ? V::load(dbase + ((int64_t)(b0 + s) * N + i) * Cout + gl * VW) : V::zero();
+    // finished dalpha (scaled by the head-mean factor) of this lane's (edge, sample) in the batch starting at `base`
+    auto batch = [&](int32_t base) -> float {
+      float p[L];
 #pragma unroll
-      for (int s = 0; s < SB; ++s) mine[s] = 0.f;
-      for (int j = 0; j < n; ++j) {
-        const int32_t c = __shfl_sync(mask, c_reg, j, L);
-        float d[SB];
+      for (int j = 0; j < NB; ++j) {
+        const int32_t k = base + j;
+        const int32_t c = k < end ? col[k] : -1;
 #pragma unroll
-        for (int s = 0; s < SB; ++s) d[s] = 0.f;
-        for (int chunk = 0; chunk < nchunks; ++chunk) {
-          const int off = (chunk * L + gl) * VW;
-          if (off < C) {
-            typename V::T zv[SB], dv[SB];
+        for (int s = 0; s < SB; ++s) p[j * SB + s] = 0.f;
+        if (c >= 0) {
+          if (one) {
+            if (gl * VW < C) {
+              typename V::T zv[SB];
 #pragma unroll
-            for (int s = 0; s < SB; ++s) {
-              if (s < nb) {
-                zv[s] = V::load(z + ((int64_t)(b0 + s) * N + c) * HC + h * C + off);
-                dv[s] = V::load(dout + ((int64_t)(b0 + s) * N + i) * Cout + (concat ? h * C : 0) + off);
+              for (int s = 0; s < SB; ++s)
+                if (s < nb) zv[s] = V::load(z + ((int64_t)(b0 + s) * N + c) * HC + h * C + gl * VW);
+#pragma unroll
+              for (int s = 0; s < SB; ++s)
+                if (s < nb) p[j * SB + s] = V::dot(dv[s], zv[s]);
+            }
+          } else {
+            for (int chunk = 0; chunk < nchunks; ++chunk) {
+              const int off = (chunk * L + gl) * VW;
+              if (off < C) {
+#pragma unroll
+                for (int s = 0; s < SB; ++s)
+                  if (s < nb)
+                    p[j * SB + s] += V::dot(V::load(dbase + ((int64_t)(b0 + s) * N + i) * Cout + off),
+                                            V::load(z + ((int64_t)(b0 + s) * N + c) * HC + h * C + off));
               }
             }
-#pragma unroll
-            for (int s = 0; s < SB; ++s)
-              if (s < nb) d[s] += V::dot(dv[s], zv[s]);
-          }
-        }
-#pragma unroll
-        for (int s = 0; s < SB; ++s) {
-          const float r = gsum<L>(d[s], mask) * hs;
-          if (gl == j) mine[s] = r;
-        }
-      }
-      if (k < end) {
-#pragma unroll
-        for (int s = 0; s < SB; ++s) {
-          if (s < nb) {
-            const int64_t idx = ((int64_t)(b0 + s) * nnz + k) * H + h;
-            t[s] += alpha_csr[idx] * mine[s];
-            if (single) keep[s] = mine[s];
-            else g_csr[idx] = mine[s];
           }
         }
       }
-    }
+      return xreduce<L>(p, gl, mask) * hs;
+    };
+
+    const float adst = s_ok ? a_dst[(bs * N + i) * H + h] : 0.f;
+    float tp = 0.f, gs = 0.f;
+    if (single) {
+      float dal[SB], al[SB];
 #pragma unroll
-    for (int s = 0; s < SB; ++s) t[s] = gsum<L>(t[s], mask);
-    float gs[SB];
+      for (int q = 0; q < SB; ++q) {
+        dal[q] = al[q] = 0.f;
+        const int32_t base = beg + q * NB;
+        if (base < end) {                                   // group-uniform
+          const float r = batch(base);
+          const int32_t k = base + jj;
+          if (k < end && s_ok) {
+            dal[q] = r;
+            al[q] = alpha_csr[(bs * nnz + k) * H + h];
+            tp += al[q] * r;
+          }
+        }
+      }
+      const float t = gsum_strided<L, SB>(tp, mask);
 #pragma unroll
-    for (int s = 0; s < SB; ++s) gs[s] = 0.f;
-    for (int32_t k = beg + gl; k < end; k += L) {
-      const int32_t c = col[k];
-#pragma unroll
-      for (int s = 0; s < SB; ++s) {
-        if (s < nb) {
-          const int64_t idx = ((int64_t)(b0 + s) * nnz + k) * H + h;
-          const float dal = single ? keep[s] : g_csr[idx];   // own write (same lane <-> same entry)
-          const float pre = a_src[((int64_t)(b0 + s) * N + c) * H + h] + a_dst[((int64_t)(b0 + s) * N + i) * H + h];
-          const float g = alpha_csr[idx] * (dal - t[s]) * (pre > 0.f ? 1.f : slope);
+      for (int q = 0; q < SB; ++q) {
+        const int32_t k = beg + q * NB + jj;
+        if (k < end && s_ok) {
+          const float pre = a_src[(bs * N + col[k]) * H + h] + adst;
+          const float g = al[q] * (dal[q] - t) * (pre > 0.f ? 1.f : slope);
+          g_csr[(bs * nnz + k) * H + h] = g;
+          gs += g;
+        }
+      }
+    } else {
+      for (int32_t base = beg; base < end; base += NB) {
+        const float r = batch(base);
+        const int32_t k = base + jj;
+        if (k < end && s_ok) {
+          const int64_t idx = (bs * nnz + k) * H + h;
+          tp += alpha_csr[idx] * r;
+          g_csr[idx] = r;                                  // staged; re-read below by the same lane
+        }
+      }
+      const float t = gsum_strided<L, SB>(tp, mask);
+      for (int32_t base = beg; base < end; base += NB) {
+        const int32_t k = base + jj;
+        if (k < end && s_ok) {
+          const int64_t idx = (bs * nnz + k) * H + h;
+          const float pre = a_src[(bs * N + col[k]) * H + h] + adst;
+          const float g = alpha_csr[idx] * (g_csr[idx] - t) * (pre > 0.f ? 1.f : slope);
           g_csr[idx] = g;
-          gs[s] += g;
+          gs += g;
         }
       }
     }
-#pragma unroll
-    for (int s = 0; s < SB; ++s) {
-      const float r = gsum<L>(gs[s], mask);
-      if (gl == 0 && s < nb) da_dst[((int64_t)(b0 + s) * N + i) * H + h] = r;
-    }
+    gs = gsum_strided<L, SB>(gs, mask);
+    if (jj == 0 && s_ok) da_dst[(bs * N + i) * H + h] = gs;
   }
 }
 

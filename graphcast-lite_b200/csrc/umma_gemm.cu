@@ -890,17 +890,30 @@ __global__ void __launch_bounds__(kLtThreads, 1)
 
 // ------------------------------------------------------------------------------------------------
 // TMA-fed dW: the copy engine brings [32 rows x M] / [32 rows x N] boxes of dY / X (row-major, unswizzled)
-// into a raw ring, the converter warps transpose + split them smem -> smem into the K-major stages (a lane
-// owns one column and four consecutive rows = one 16-byte K chunk, both sides conflict-free), so no global
-// load latency sits on any warp's critical path.  Row tails are zero-filled by the tensor map.
-__global__ void __launch_bounds__(kThreads, 1)
+// into a raw ring; converter warps transpose + split them smem -> smem into the K-major stages.  A "unit" is
+// 32 columns x 4 rows: a lane owns one column, reads it for 4 consecutive rows (4 conflict-free LDS.32) and
+// that is exactly one 16-byte K chunk of that column's row in the SWIZZLE_128B K-major layout (consecutive
+// lanes -> different swizzled chunks, conflict-free STS.128).  No global-load latency sits on any warp.
+// The converters were instruction-bound with generic per-unit index math, so every warp precomputes its <= NU
+// units (source / destination offsets) once and the K-block loop is 4 LDS + split + 2 STS per unit.
+// 18 warps: 0-3 convert, then run the epilogue; 4 MMA issue + TMEM; 5 TMA producer; 6-17 convert.
+constexpr int kDwWarps = 18, kDwThreads = kDwWarps * 32, kDwConv = 16;
+#ifndef GCL_DW_GROUPS
+#define GCL_DW_GROUPS 2
+#endif
+constexpr int kDwGroups = GCL_DW_GROUPS;
+
+template <int NU>
+__global__ void __launch_bounds__(kDwThreads, 1)
     umma_dw_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        float* __restrict__ part, float* __restrict__ part_colsum, int64_t R, int M, int N, int n_pad,
                        int nst, int nraw, int raw_bytes, int tmem_cols, int64_t rows_per_cta) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_part = n_pad * 128;
-  const int stage_bytes = 2 * kPartBytes + 2 * b_part;
+  // the A parts hold only ceil(M / 8) * 8 rows: the M = 128 MMA also reads the following 128 - that rows of
+  // whatever comes next in smem, which only produces accumulator rows >= M that nobody reads
+  const int a_part = ((M + 7) / 8) * 8 * 128, b_part = n_pad * 128;
+  const int stage_bytes = 2 * a_part + 2 * b_part;
   uint8_t* st_base = smem;
   uint8_t* raw = st_base + (size_t)nst * stage_bytes;
   uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(raw + (size_t)nraw * raw_bytes);
@@ -915,22 +928,22 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (tid == 0) {
     for (int s = 0; s < nst; ++s) {
-      mbar_init(bar(kFull + s), kDwConvWarps * 32);
+      mbar_init(bar(kFull + s), kDwConv / kDwGroups);      // one arrival per converter warp of the K-block's group
       mbar_init(bar(kEmpty + s), 1);
     }
     for (int s = 0; s < nraw; ++s) {
       mbar_init(bar(kRawFull + s), 1);
-      mbar_init(bar(kRawEmpty + s), kDwConvWarps * 32);
+      mbar_init(bar(kRawEmpty + s), kDwConv / kDwGroups);
     }
     mbar_init(bar(kAccFull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kEpiWarps) tmem_alloc(smem_u32(tmem_slot), (uint32_t)tmem_cols);
-  for (int i = tid; i < nst * stage_bytes / 16; i += kThreads)
+  for (int i = tid; i < nst * stage_bytes / 16; i += kDwThreads)
     reinterpret_cast<float4*>(st_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  for (int i = tid; i < nst * 8; i += kThreads) {
-    uint8_t* b_hi = st_base + (size_t)(i >> 3) * stage_bytes + 2 * kPartBytes;
+  for (int i = tid; i < nst * 8; i += kDwThreads) {
+    uint8_t* b_hi = st_base + (size_t)(i >> 3) * stage_bytes + 2 * a_part;
     *reinterpret_cast<float4*>(b_hi + sw_off(N, i & 7)) = make_float4(1.f, 1.f, 1.f, 1.f);
   }
   fence_proxy_async();
@@ -954,56 +967,66 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp != kEpiWarps) {
-    // converters: warps 0-3 (which run the epilogue afterwards) and 6-11
-    const int cw = warp < kEpiWarps ? warp : warp - 2;     // 0..9
+    // converter warp cw belongs to group cw % kDwGroups, which handles the K-blocks kb % kDwGroups == group:
+    // a group may take kDwGroups K-block times for its wait -> load -> split -> store -> fence -> arrive chain
+    const int cw = warp < kEpiWarps ? warp : warp - 2;     // 0..15
+    const int grp = cw % kDwGroups, wi = cw / kDwGroups;   // wi: 0 .. kDwConv / kDwGroups - 1
     const int na_units = 8 * ((M + 31) / 32), n_units = na_units + 8 * ((N + 31) / 32);
+    // this warp's units: byte offsets into a raw stage / a K-major stage (hi part), row pitch, hi -> lo distance
+    uint32_t src_off[NU], dst_off[NU], pitch[NU], lo_off[NU];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      const int u = wi + i * (kDwConv / kDwGroups);
+      const bool isa = u < na_units;
+      const int uu = isa ? u : u - na_units;
+      const int width = isa ? M : N;
+      const int col = (uu >> 3) * 32 + lane, chunk = uu & 7;
+      const bool ok = u < n_units && col < width;
+      pitch[i] = (uint32_t)width * 4;
+      src_off[i] = ok ? (uint32_t)((isa ? 0 : kKB * M * 4) + ((chunk * 4) * width + col) * 4) : 0xffffffffu;
+      dst_off[i] = (uint32_t)(isa ? 0 : 2 * a_part) + sw_off(col, chunk);
+      lo_off[i] = isa ? (uint32_t)a_part : (uint32_t)b_part;
+    }
     const uint32_t st_u32 = smem_u32(st_base), raw_u32 = smem_u32(raw);
-    int st = 0, rs = 0;
+    int st = grp % nst, rs = grp % nraw;                  // kDwGroups <= nst, nraw (host guarantees)
     uint32_t ph = 1, rph = 0;
-    constexpr int kBatch = 4;                              // units in flight per warp (16 LDS.32)
-    for (int64_t kb = 0; kb < nkb; ++kb) {
+    for (int64_t kb = grp; kb < nkb; kb += kDwGroups) {
       mbar_wait(bar(kRawFull + rs), rph);
       mbar_wait(bar(kEmpty + st), ph);
-      const uint32_t ra = raw_u32 + (uint32_t)rs * (uint32_t)raw_bytes, rb = ra + (uint32_t)(kKB * M * 4);
-      const uint32_t a_hi = st_u32 + (uint32_t)st * (uint32_t)stage_bytes;
-      const uint32_t b_hi = a_hi + 2 * kPartBytes;
-      for (int u0 = cw; u0 < n_units; u0 += kBatch * kDwConvWarps) {
-        float4 v[kBatch];
-        uint32_t dst[kBatch];
+      const uint32_t rbase = raw_u32 + (uint32_t)rs * (uint32_t)raw_bytes;
+      const uint32_t sbase = st_u32 + (uint32_t)st * (uint32_t)stage_bytes;
+      float4 v[NU];
+#ifndef GCL_DW_SKIP_CONV
 #pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-          const int u = u0 + i * kDwConvWarps;
-          const bool isa = u < na_units;
-          const int uu = isa ? u : u - na_units;
-          const int width = isa ? M : N;
-          const int col = (uu >> 3) * 32 + lane, chunk = uu & 7;
-          dst[i] = 0xffffffffu;
-          if (u < n_units && col < width) {
-            const uint32_t src = (isa ? ra : rb) + (uint32_t)(((chunk * 4) * width + col) * 4);
-            const uint32_t w4 = (uint32_t)width * 4;
-            v[i] = make_float4(lds_f32(src), lds_f32(src + w4), lds_f32(src + 2 * w4), lds_f32(src + 3 * w4));
-            dst[i] = (isa ? a_hi : b_hi) + sw_off(col, chunk);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-          if (dst[i] != 0xffffffffu) {
-            const int u = u0 + i * kDwConvWarps;
-            float4 h, l;
-            split_tf32(v[i].x, h.x, l.x);
-            split_tf32(v[i].y, h.y, l.y);
-            split_tf32(v[i].z, h.z, l.z);
-            split_tf32(v[i].w, h.w, l.w);
-            sts_f32x4(dst[i], h);
-            sts_f32x4(dst[i] + (u < na_units ? (uint32_t)kPartBytes : (uint32_t)b_part), l);
-          }
+      for (int i = 0; i < NU; ++i) {
+        if (src_off[i] != 0xffffffffu) {
+          const uint32_t a = rbase + src_off[i];
+          v[i] = make_float4(lds_f32(a), lds_f32(a + pitch[i]), lds_f32(a + 2 * pitch[i]), lds_f32(a + 3 * pitch[i]));
         }
       }
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        if (src_off[i] != 0xffffffffu) {
+          float4 h, l;
+          split_tf32(v[i].x, h.x, l.x);
+          split_tf32(v[i].y, h.y, l.y);
+          split_tf32(v[i].z, h.z, l.z);
+          split_tf32(v[i].w, h.w, l.w);
+          sts_f32x4(sbase + dst_off[i], h);
+          sts_f32x4(sbase + dst_off[i] + lo_off[i], l);
+        }
+      }
+#endif
       fence_proxy_async();
-      mbar_arrive(bar(kFull + st));
-      mbar_arrive(bar(kRawEmpty + rs));
-      if (++st == nst) { st = 0; ph ^= 1; }
-      if (++rs == nraw) { rs = 0; rph ^= 1; }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(kFull + st));
+        mbar_arrive(bar(kRawEmpty + rs));
+      }
+      st += kDwGroups;
+      if (st >= nst) { st -= nst; ph ^= 1; }
+      rs += kDwGroups;
+      if (rs >= nraw) { rs -= nraw; rph ^= 1; }
     }
     if (warp < kEpiWarps) {
       // ---- epilogue: the accumulator is complete once the last MMA has retired
@@ -1014,14 +1037,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
         for (int c0 = 0; c0 < n_pad; c0 += 16) {
-          float v[16];
-          tmem_ld16(taddr + c0, v);
+          float v16[16];
+          tmem_ld16(taddr + c0, v16);
           if (m < M) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int n = c0 + j;
-              if (n < N) prow[n] = v[j];
-              else if (n == N && part_colsum) part_colsum[(int64_t)blockIdx.x * M + m] = v[j];
+              if (n < N) prow[n] = v16[j];
+              else if (n == N && part_colsum) part_colsum[(int64_t)blockIdx.x * M + m] = v16[j];
             }
           }
         }
@@ -1030,7 +1053,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (part_colsum) part_colsum[(int64_t)blockIdx.x * M + m] = 0.f;
       }
     }
-  } else if (warp == kEpiWarps) {
+  } else {
     const uint32_t idesc = make_idesc(n_pad, 0, 0);
     const uint32_t st_lo = desc_lo(smem_u32(st_base));
     int st = 0;
@@ -1039,11 +1062,15 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_wait(bar(kFull + st), ph);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t ah = st_lo + (uint32_t)st * ((uint32_t)stage_bytes >> 4), al = ah + (kPartBytes >> 4);
-        const uint32_t bh = al + (kPartBytes >> 4), bl = bh + ((uint32_t)b_part >> 4);
+        const uint32_t ah = st_lo + (uint32_t)st * ((uint32_t)stage_bytes >> 4), al = ah + ((uint32_t)a_part >> 4);
+        const uint32_t bh = al + ((uint32_t)a_part >> 4), bl = bh + ((uint32_t)b_part >> 4);
+#ifndef GCL_DW_SKIP_MMA
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
           umma_3x(tmem_base, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+#else
+        if (kb == 0) umma_3x(tmem_base, ah, al, bh, bl, idesc, 0u);
+#endif
         umma_commit(bar(kEmpty + st));
         if (kb == nkb - 1) umma_commit(bar(kAccFull));
       }
@@ -1267,23 +1294,36 @@ int umma_dw(const float* A, const float* B, float* part, float* part_colsum, int
   if (!g_force_register_staging && (M & 3) == 0 && (N & 3) == 0 && al16(A) && al16(B) && R <= 0x7fffff00LL) {
     // raw ring + as many K-major stages as fit
     const int raw_bytes = (int)((kKB * (M + N) * 4 + 127) / 128 * 128);
-    const size_t stage = 2 * (size_t)kPartBytes + 2 * (size_t)p.n_pad * 128;
+    const size_t stage = 2 * (size_t)((M + 7) / 8 * 8) * 128 + 2 * (size_t)p.n_pad * 128;
     const size_t fixed = 1024 + 512;
-    int nst = 3, nraw = 0;
+    static const int kDwMinRaw = getenv("GCL_DW_MINRAW") ? atoi(getenv("GCL_DW_MINRAW")) : 6;
+    int nst = 4, nraw = 0;
     for (; nst >= 2; --nst) {
       const long room = (long)kMaxSmem - (long)fixed - (long)nst * (long)stage;
       nraw = room > 0 ? (int)(room / raw_bytes) : 0;
-      if (nraw >= 3 || (nst == 2 && nraw >= 2)) break;
+      if (nraw >= kDwMinRaw || (nst == 2 && nraw >= 2)) break;
     }
-    if (nraw > 8) nraw = 8;
+    if (nraw > 10) nraw = 10;
     CUtensorMap tmA, tmB;
-    if (nst >= 2 && nraw >= 2 && make_map_2d(&tmA, A, R, M, kKB, (int)M, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+    if (nst >= kDwGroups && nraw >= kDwGroups && nst >= 2 && nraw >= 2 && (size_t)nraw * raw_bytes >= (size_t)kPartBytes && make_map_2d(&tmA, A, R, M, kKB, (int)M, CU_TENSOR_MAP_SWIZZLE_NONE) &&
         make_map_2d(&tmB, B, R, N, kKB, (int)N, CU_TENSOR_MAP_SWIZZLE_NONE)) {
       const size_t smem = fixed + (size_t)nst * stage + (size_t)nraw * raw_bytes;
-      cudaError_t e = cudaFuncSetAttribute(umma_dw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return fail_cuda(e, "umma_dw_tma(smem attr)");
-      umma_dw_tma_kernel<<<p.grid, kThreads, smem, s>>>(tmA, tmB, part, part_colsum, R, (int)M, (int)N, p.n_pad, nst, nraw,
-                                                        raw_bytes, p.tmem_cols, p.rows_per_cta);
+      const int per_grp = kDwConv / kDwGroups;
+      const int n_units = 8 * (int)((M + 31) / 32 + (N + 31) / 32), nu = (n_units + per_grp - 1) / per_grp;
+      auto launch = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail_cuda(e, "umma_dw_tma(smem attr)");
+        kern<<<p.grid, kDwThreads, smem, s>>>(tmA, tmB, part, part_colsum, R, (int)M, (int)N, p.n_pad, nst, nraw,
+                                              raw_bytes, p.tmem_cols, p.rows_per_cta);
+        return GCL_OK;
+      };
+      int rc;
+      if (nu <= 2) rc = launch(umma_dw_tma_kernel<2>);
+      else if (nu <= 4) rc = launch(umma_dw_tma_kernel<4>);
+      else if (nu <= 6) rc = launch(umma_dw_tma_kernel<6>);
+      else if (nu <= 8) rc = launch(umma_dw_tma_kernel<8>);
+      else rc = launch(umma_dw_tma_kernel<16>);
+      if (rc != GCL_OK) return rc;
       GCL_CHECK_LAUNCH("umma_dw_tma");
       return GCL_OK;
     }
