@@ -259,12 +259,14 @@ def run_gcl(args):
     peak, peak_src = measured_peak_gbs()
     roof, by_kernel, edges = None, [], None
     if rank == 0 and args.profile_steps > 0:
+        world_saved, tr.world = tr.world, 1         # rank 0 profiles alone: no collective in these eager steps
         tr.step(tr.static_x, tr.static_y)           # eager warm-up
         ops.PROFILER = ops.KernelProfiler()
         for _ in range(args.profile_steps):
             tr.step(tr.static_x, tr.static_y)
         agg = ops.PROFILER.summary()
         ops.PROFILER = None
+        tr.world = world_saved
         total = sum(a["ms"] for a in agg.values()) or 1.0
         rows = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
         for (name, tag), a in rows[:args.kernel_rows]:
@@ -304,7 +306,7 @@ def run_gcl(args):
                        "cuda_graph": "fwd+bwd captured; all-reduce + Adam eager"},
             "clocks": clocks,
             "e2e": {"value": world * B / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
-                    "h2d_bytes_per_step": int(hx.numel() + hy.numel()) * 4, "d2h_bytes_per_step": 4,
+                    "h2d_bytes_per_step": world * int(hx.numel() + hy.numel()) * 4, "d2h_bytes_per_step": world * 4,
                     "api": "gcl_b200.train.Trainer.step_from_host(X_pinned, y_pinned) -> float loss"},
             "gpu_launches": int(tr.launches_in_graph * args.steps + eager_launches),
             "gpu_launches_per_step": int(tr.launches_in_graph + eager_launches // max(args.steps, 1)),

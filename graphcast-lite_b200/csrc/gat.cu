@@ -534,14 +534,69 @@ __global__ void gat_datt_partial_kernel(const float* __restrict__ z, const float
   }
 }
 
+// 128-bit version (C % 4 == 0, H C <= 1024, 16-byte aligned z): float4 column groups x row lanes, 4 rows in flight.
+__global__ void __launch_bounds__(256)
+    gat_datt_partial_v4_kernel(const float4* __restrict__ z, const float* __restrict__ da_src,
+                               const float* __restrict__ da_dst, float* __restrict__ part, int64_t rows, int H, int C,
+                               int64_t rows_per_block) {
+  __shared__ float4 sm[2][256];
+  const int HC = H * C, ncol = HC >> 2, lanes = 256 / ncol, tid = threadIdx.x;
+  const int ci = tid % ncol, rl = tid / ncol, h = (4 * ci) / C;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), d = s;
+  if (rl < lanes) {
+    for (int64_t r = r0 + rl; r < r1; r += 4 * lanes) {
+      float4 v[4];
+      float as[4], ad[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t rr = r + (int64_t)u * lanes;
+        const bool ok = rr < r1;
+        v[u] = ok ? __ldg(z + rr * ncol + ci) : make_float4(0.f, 0.f, 0.f, 0.f);
+        as[u] = ok ? __ldg(da_src + rr * H + h) : 0.f;
+        ad[u] = ok ? __ldg(da_dst + rr * H + h) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s.x = fmaf(as[u], v[u].x, s.x); s.y = fmaf(as[u], v[u].y, s.y);
+        s.z = fmaf(as[u], v[u].z, s.z); s.w = fmaf(as[u], v[u].w, s.w);
+        d.x = fmaf(ad[u], v[u].x, d.x); d.y = fmaf(ad[u], v[u].y, d.y);
+        d.z = fmaf(ad[u], v[u].z, d.z); d.w = fmaf(ad[u], v[u].w, d.w);
+      }
+    }
+  }
+  sm[0][tid] = s;
+  sm[1][tid] = d;
+  __syncthreads();
+  if (tid < 2 * ncol) {
+    const int which = tid / ncol, cc = tid % ncol;
+    float4 t = sm[which][cc];
+    for (int l = 1; l < lanes; ++l) {
+      const float4 o = sm[which][l * ncol + cc];
+      t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+    }
+    float* dst = part + ((int64_t)blockIdx.x * 2 + which) * HC + 4 * cc;
+    dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+  }
+}
+
+// out[i] = sum_k part[k * 2n + i], fixed order (8 interleaved partial sums, then ascending); block (32, 8)
 __global__ void reduce2_kernel(const float* __restrict__ part, int nblk, int n, float* __restrict__ out0,
                                float* __restrict__ out1) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * n) return;
+  __shared__ float sm[8][33];
+  const int i = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int k = 0; k < nblk; ++k) s += part[(int64_t)k * 2 * n + i];
-  if (i < n) out0[i] = s;
-  else out1[i - n] = s;
+  if (i < 2 * n)
+    for (int k = threadIdx.y; k < nblk; k += 8) s += part[(int64_t)k * 2 * n + i];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < 2 * n) {
+    float t = sm[0][threadIdx.x];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) t += sm[y][threadIdx.x];
+    if (i < n) out0[i] = t;
+    else out1[i - n] = t;
+  }
 }
 
 __global__ void prune_flags_kernel(const float* __restrict__ alpha, int64_t nnz, float thr,
@@ -689,10 +744,14 @@ extern "C" int gcl_gat_datt_f32(const float* z, const float* da_src, const float
   }
   Plan pl = rows_plan(rows);
   float* part = static_cast<float*>(workspace);
-  gat_datt_partial_kernel<<<pl.nblk, dim3(32, 8), 0, s>>>(z, da_src, da_dst, part, rows, (int)heads, (int)c,
-                                                          pl.rows_per_block);
+  if ((c & 3) == 0 && HC <= 1024 && 2 * (HC >> 2) <= 256 && (reinterpret_cast<uintptr_t>(z) & 15u) == 0)
+    gat_datt_partial_v4_kernel<<<pl.nblk, 256, 0, s>>>(reinterpret_cast<const float4*>(z), da_src, da_dst, part, rows,
+                                                       (int)heads, (int)c, pl.rows_per_block);
+  else
+    gat_datt_partial_kernel<<<pl.nblk, dim3(32, 8), 0, s>>>(z, da_src, da_dst, part, rows, (int)heads, (int)c,
+                                                            pl.rows_per_block);
   GCL_CHECK_LAUNCH("gcl_gat_datt_f32(partial)");
-  reduce2_kernel<<<(unsigned)ceil_div(2 * HC, 256), 256, 0, s>>>(part, pl.nblk, HC, datt_src, datt_dst);
+  reduce2_kernel<<<(unsigned)ceil_div(2 * HC, 32), dim3(32, 8), 0, s>>>(part, pl.nblk, HC, datt_src, datt_dst);
   GCL_CHECK_LAUNCH("gcl_gat_datt_f32(reduce)");
   return GCL_OK;
 }
