@@ -265,6 +265,120 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- 128-bit LayerNorm (C % 4 == 0, C <= 128, 16-byte aligned rows) ---------------------------------------------
+// L = 8 / 16 / 32 lanes per row, a lane holds one float4 of it; a block owns a contiguous row range and each lane
+// group keeps two rows in flight.  (The warp-per-row scalar kernels below ran at ~0.4 of the HBM roofline: one
+// 4-byte load per lane and row, and a warp retired after a single row.)
+template <int L>
+__device__ __forceinline__ float lsum(float v) {
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, L);
+  return v;
+}
+__device__ __forceinline__ float hsum4(float4 v) { return (v.x + v.y) + (v.z + v.w); }
+
+template <int L>
+__global__ void __launch_bounds__(256)
+    layernorm_fwd_v4_kernel(const float4* __restrict__ x, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, float4* __restrict__ y, float* __restrict__ mean_out,
+                            float* __restrict__ rstd_out, int64_t rows, int C, float eps, int64_t rows_per_block) {
+  constexpr int kGroups = 256 / L;
+  const int tid = threadIdx.x, gl = tid & (L - 1), grp = tid / L, ncol = C >> 2;
+  const bool live = gl < ncol;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (gamma && live) {
+    g4 = __ldg(reinterpret_cast<const float4*>(gamma) + gl);
+    b4 = __ldg(reinterpret_cast<const float4*>(beta) + gl);
+  }
+  const float inv_c = 1.f / (float)C;
+  for (int64_t base = r0; base < r1; base += 2 * kGroups) {   // block-uniform trip count
+    float4 v[2];
+    int64_t row[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      row[u] = base + u * kGroups + grp;
+      v[u] = (live && row[u] < r1) ? __ldcs(x + row[u] * ncol + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float mean = lsum<L>(hsum4(v[u])) * inv_c;
+      const float4 d = live ? make_float4(v[u].x - mean, v[u].y - mean, v[u].z - mean, v[u].w - mean)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float rstd = rsqrtf(lsum<L>((d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w)) * inv_c + eps);
+      if (row[u] < r1) {
+        if (live)
+          y[row[u] * ncol + gl] = make_float4(d.x * rstd * g4.x + b4.x, d.y * rstd * g4.y + b4.y,
+                                              d.z * rstd * g4.z + b4.z, d.w * rstd * g4.w + b4.w);
+        if (gl == 0) {
+          if (mean_out) mean_out[row[u]] = mean;
+          if (rstd_out) rstd_out[row[u]] = rstd;
+        }
+      }
+    }
+  }
+}
+
+template <int L>
+__global__ void __launch_bounds__(256)
+    layernorm_bwd_v4_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
+                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                            const float* __restrict__ rstd, float4* __restrict__ dx, float* __restrict__ part,
+                            int64_t rows, int C, int64_t rows_per_block) {
+  constexpr int kGroups = 256 / L;
+  __shared__ float4 sm[2][256];
+  const int tid = threadIdx.x, gl = tid & (L - 1), grp = tid / L, ncol = C >> 2;
+  const bool live = gl < ncol;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  const float4 gm = (gamma && live) ? __ldg(reinterpret_cast<const float4*>(gamma) + gl)
+                                    : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float inv_c = 1.f / (float)C;
+  float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
+  for (int64_t base = r0; base < r1; base += 2 * kGroups) {
+    float4 d[2], xv[2];
+    float mu[2], rs[2];
+    int64_t row[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      row[u] = base + u * kGroups + grp;
+      const bool ok = live && row[u] < r1;
+      d[u] = ok ? __ldcs(dy + row[u] * ncol + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xv[u] = ok ? __ldcs(x + row[u] * ncol + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mu[u] = row[u] < r1 ? __ldg(mean + row[u]) : 0.f;
+      rs[u] = row[u] < r1 ? __ldg(rstd + row[u]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const bool ok = live && row[u] < r1;
+      const float4 xh = ok ? make_float4((xv[u].x - mu[u]) * rs[u], (xv[u].y - mu[u]) * rs[u],
+                                         (xv[u].z - mu[u]) * rs[u], (xv[u].w - mu[u]) * rs[u])
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 g = make_float4(d[u].x * gm.x, d[u].y * gm.y, d[u].z * gm.z, d[u].w * gm.w);
+      dg.x += d[u].x * xh.x; dg.y += d[u].y * xh.y; dg.z += d[u].z * xh.z; dg.w += d[u].w * xh.w;
+      db.x += d[u].x; db.y += d[u].y; db.z += d[u].z; db.w += d[u].w;
+      const float s1 = lsum<L>(hsum4(g)) * inv_c;
+      const float s2 = lsum<L>((g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w)) * inv_c;
+      if (ok)
+        dx[row[u] * ncol + gl] = make_float4(rs[u] * (g.x - s1 - xh.x * s2), rs[u] * (g.y - s1 - xh.y * s2),
+                                             rs[u] * (g.z - s1 - xh.z * s2), rs[u] * (g.w - s1 - xh.w * s2));
+    }
+  }
+  if (part == nullptr) return;
+  sm[0][tid] = dg;
+  sm[1][tid] = db;
+  __syncthreads();
+  if (tid < 2 * ncol) {
+    const int which = tid / ncol, cc = tid % ncol;
+    float4 t = sm[which][cc];
+    for (int g = 1; g < kGroups; ++g) {
+      const float4 o = sm[which][g * L + cc];
+      t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+    }
+    float* dst = part + ((int64_t)blockIdx.x * 2 + which) * C + 4 * cc;
+    dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+  }
+}
+
 // out[i] = sum_k part[k * n + i] in a fixed order (8 interleaved partial sums, then those 8 ascending); block
 // (32, 8) per 32 outputs.  Columns < C go to out0, the rest to out1.
 __global__ void reduce_cols_kernel(const float* __restrict__ part, int nblk, int n, float* __restrict__ out0,
@@ -389,6 +503,18 @@ extern "C" int gcl_layernorm_fwd_f32(const float* x, const float* gamma, const f
   }
   if (rows == 0) return GCL_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+                    reinterpret_cast<uintptr_t>(beta)) & 15u) == 0;
+  if ((c & 3) == 0 && c <= 128 && al) {
+    const LnPlan pl = ln_plan(rows);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    if (c <= 32) layernorm_fwd_v4_kernel<8><<<pl.nblk, 256, 0, s>>>(x4, gamma, beta, y4, mean, rstd, rows, (int)c, eps, pl.rows_per_block);
+    else if (c <= 64) layernorm_fwd_v4_kernel<16><<<pl.nblk, 256, 0, s>>>(x4, gamma, beta, y4, mean, rstd, rows, (int)c, eps, pl.rows_per_block);
+    else layernorm_fwd_v4_kernel<32><<<pl.nblk, 256, 0, s>>>(x4, gamma, beta, y4, mean, rstd, rows, (int)c, eps, pl.rows_per_block);
+    GCL_CHECK_LAUNCH("gcl_layernorm_fwd_f32(v4)");
+    return GCL_OK;
+  }
   const unsigned grid = (unsigned)ceil_div(rows * 32, 256);
   if (c <= 128) layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, (int)c, eps);
   else if (c <= 256) layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, (int)c, eps);
@@ -428,7 +554,16 @@ extern "C" int gcl_layernorm_bwd_f32(const float* dy, const float* x, const floa
   float* part = want_params ? static_cast<float*>(workspace) : nullptr;
   const size_t smem = (size_t)8 * 2 * c * sizeof(float);
   const int C = (int)c;
-  if (c <= 128)
+  const bool al = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
+                    reinterpret_cast<uintptr_t>(gamma)) & 15u) == 0;
+  if ((c & 3) == 0 && c <= 128 && al) {
+    const float4* dy4 = reinterpret_cast<const float4*>(dy);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* dx4 = reinterpret_cast<float4*>(dx);
+    if (c <= 32) layernorm_bwd_v4_kernel<8><<<pl.nblk, 256, 0, s>>>(dy4, x4, gamma, mean, rstd, dx4, part, rows, C, pl.rows_per_block);
+    else if (c <= 64) layernorm_bwd_v4_kernel<16><<<pl.nblk, 256, 0, s>>>(dy4, x4, gamma, mean, rstd, dx4, part, rows, C, pl.rows_per_block);
+    else layernorm_bwd_v4_kernel<32><<<pl.nblk, 256, 0, s>>>(dy4, x4, gamma, mean, rstd, dx4, part, rows, C, pl.rows_per_block);
+  } else if (c <= 128)
     layernorm_bwd_kernel<4><<<pl.nblk, 256, smem, s>>>(dy, x, gamma, mean, rstd, dx, part, rows, C, pl.rows_per_block);
   else if (c <= 256)
     layernorm_bwd_kernel<8><<<pl.nblk, 256, smem, s>>>(dy, x, gamma, mean, rstd, dx, part, rows, C, pl.rows_per_block);
