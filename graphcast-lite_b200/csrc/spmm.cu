@@ -50,7 +50,7 @@ template <int VW, int L, int SB>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                 const float* __restrict__ w, const float* __restrict__ x, float* __restrict__ out,
-                int64_t n_rows, int C, int nchunks, int64_t x_bstride, int64_t out_bstride, int B,
+                int64_t n_rows, int64_t n_in, int C, int nchunks, int64_t x_bstride, int64_t out_bstride, int B,
                 const float* __restrict__ bias, const float* __restrict__ prelu_slope,
                 float* __restrict__ z_out) {
   using V = Vec<VW>;
@@ -79,6 +79,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     if (gl < n) {
       c_reg = __ldg(col + base + gl);
       w_reg = w ? __ldg(w + base + gl) : 1.f;
+      if (c_reg >= n_in) {   // entry points past the rows x holds (output restricted to a row prefix): a zero row
+        c_reg = 0;
+        w_reg = 0.f;
+      }
     }
 #pragma unroll 2
     for (int j = 0; j < n; ++j) {
@@ -123,14 +127,14 @@ inline int pick_sb(int64_t B, int64_t n_rows, int64_t C, int64_t nnz) {
 
 template <int VW, int L, int SB>
 int launch(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, float* out, int64_t B,
-           int64_t n_rows, int64_t C, int64_t xbs, int64_t obs, const float* bias, const float* slope,
+           int64_t n_rows, int64_t n_in, int64_t C, int64_t xbs, int64_t obs, const float* bias, const float* slope,
            float* z_out, cudaStream_t s) {
   const int64_t units = ceil_div(C, VW);          // vector words per row
   const int nchunks = (int)ceil_div(units, 32);
   const int64_t items = n_rows * nchunks;
   const int64_t per_block = (int64_t)kWarpsPerBlock * (32 / L);
   dim3 grid((unsigned)ceil_div(items, per_block), (unsigned)ceil_div(B, SB));
-  spmm_kernel<VW, L, SB><<<grid, kWarpsPerBlock * 32, 0, s>>>(rowptr, col, w, x, out, n_rows, (int)C, nchunks,
+  spmm_kernel<VW, L, SB><<<grid, kWarpsPerBlock * 32, 0, s>>>(rowptr, col, w, x, out, n_rows, n_in, (int)C, nchunks,
                                                              xbs, obs, (int)B, bias, slope, z_out);
   GCL_CHECK_LAUNCH("gcl_spmm_f32");
   return GCL_OK;
@@ -138,23 +142,23 @@ int launch(const int32_t* rowptr, const int32_t* col, const float* w, const floa
 
 template <int VW, int L>
 int dispatch_sb(int sb, const int32_t* rowptr, const int32_t* col, const float* w, const float* x, float* out,
-                int64_t B, int64_t n_rows, int64_t C, int64_t xbs, int64_t obs, const float* bias,
+                int64_t B, int64_t n_rows, int64_t n_in, int64_t C, int64_t xbs, int64_t obs, const float* bias,
                 const float* slope, float* z_out, cudaStream_t s) {
-  if (sb >= 8) return launch<VW, L, 8>(rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
-  if (sb >= 4) return launch<VW, L, 4>(rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
-  if (sb >= 2) return launch<VW, L, 2>(rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
-  return launch<VW, L, 1>(rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
+  if (sb >= 8) return launch<VW, L, 8>(rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
+  if (sb >= 4) return launch<VW, L, 4>(rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
+  if (sb >= 2) return launch<VW, L, 2>(rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
+  return launch<VW, L, 1>(rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
 }
 
 template <int VW>
 int dispatch_l(int64_t units, const int32_t* rowptr, const int32_t* col, const float* w, const float* x,
-               float* out, int64_t B, int64_t n_rows, int64_t C, int64_t xbs, int64_t obs, const float* bias,
+               float* out, int64_t B, int64_t n_rows, int64_t n_in, int64_t C, int64_t xbs, int64_t obs, const float* bias,
                const float* slope, float* z_out, int64_t nnz, cudaStream_t s) {
   const int sb = pick_sb(B, n_rows, C, nnz);
-  if (units <= 4) return dispatch_sb<VW, 4>(sb, rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
-  if (units <= 8) return dispatch_sb<VW, 8>(sb, rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
-  if (units <= 16) return dispatch_sb<VW, 16>(sb, rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
-  return dispatch_sb<VW, 32>(sb, rowptr, col, w, x, out, B, n_rows, C, xbs, obs, bias, slope, z_out, s);
+  if (units <= 4) return dispatch_sb<VW, 4>(sb, rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
+  if (units <= 8) return dispatch_sb<VW, 8>(sb, rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
+  if (units <= 16) return dispatch_sb<VW, 16>(sb, rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
+  return dispatch_sb<VW, 32>(sb, rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
 }
 
 }  // namespace
@@ -163,7 +167,7 @@ int dispatch_l(int64_t units, const int32_t* rowptr, const int32_t* col, const f
 using namespace gcl;
 
 extern "C" int gcl_spmm_f32(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, float* out,
-                            int64_t batch, int64_t n_rows_out, int64_t channels, int64_t x_bstride,
+                            int64_t batch, int64_t n_rows_out, int64_t n_rows_in, int64_t channels, int64_t x_bstride,
                             int64_t out_bstride, const float* bias, const float* prelu_slope, float* z_out,
                             int64_t nnz, void* stream) {
   GCL_CHECK_ARG(rowptr && col && x && out, "gcl_spmm_f32: null pointer argument");
@@ -171,6 +175,7 @@ extern "C" int gcl_spmm_f32(const int32_t* rowptr, const int32_t* col, const flo
   GCL_CHECK_ARG(batch >= 0 && n_rows_out >= 0 && channels > 0 && channels < (1 << 20),
                 "gcl_spmm_f32: bad sizes (batch %lld rows %lld channels %lld)", (long long)batch,
                 (long long)n_rows_out, (long long)channels);
+  GCL_CHECK_ARG(n_rows_in > 0, "gcl_spmm_f32: n_rows_in must be positive");
   GCL_CHECK_ARG(batch <= 65535, "gcl_spmm_f32: batch %lld exceeds 65535", (long long)batch);
   if (batch == 0 || n_rows_out == 0) return GCL_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -178,8 +183,8 @@ extern "C" int gcl_spmm_f32(const int32_t* rowptr, const int32_t* col, const flo
   const bool vec = (channels % 4 == 0) && (x_bstride % 4 == 0) && (out_bstride % 4 == 0) && al16(x) && al16(out) &&
                    (!bias || al16(bias)) && (!z_out || al16(z_out));
   if (vec)
-    return dispatch_l<4>(channels / 4, rowptr, col, w, x, out, batch, n_rows_out, channels, x_bstride,
+    return dispatch_l<4>(channels / 4, rowptr, col, w, x, out, batch, n_rows_out, n_rows_in, channels, x_bstride,
                          out_bstride, bias, prelu_slope, z_out, nnz, s);
-  return dispatch_l<1>(channels, rowptr, col, w, x, out, batch, n_rows_out, channels, x_bstride, out_bstride,
+  return dispatch_l<1>(channels, rowptr, col, w, x, out, batch, n_rows_out, n_rows_in, channels, x_bstride, out_bstride,
                        bias, prelu_slope, z_out, nnz, s);
 }

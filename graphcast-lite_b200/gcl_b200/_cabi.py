@@ -20,7 +20,7 @@ _PROTOS = {
     "gcl_csr_workspace_bytes": (SZ, [I64, I64]),
     "gcl_csr_build": (c_int, [P, P, I64, I64, I32, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
     "gcl_csr_weights": (c_int, [P, P, P, P, P, I64, I64, I32, P, P, P, P]),
-    "gcl_spmm_f32": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
+    "gcl_spmm_f32": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "gcl_linear_fwd_f32": (c_int, [P, P, P, P, I64, I64, I64, P, P, P, P]),
     "gcl_linear_bwd_dx_f32": (c_int, [P, P, P, I64, I64, I64, P, P]),
     "gcl_set_dense_mode": (c_int, [I32]),
@@ -54,7 +54,7 @@ _PROTOS = {
     "gcl_adam_f32": (c_int, [P, P, P, P, I64, F32, F32, F32, F32, F32, P, P]),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 def lib_path() -> str:

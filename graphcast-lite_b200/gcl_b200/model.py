@@ -15,6 +15,7 @@ from typing import Optional
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _cabi, ops
 from .graph import CSR_LOOPS, CSR_RAW, GLOBAL_CACHE, NORM_GCN, NORM_MEAN
@@ -110,7 +111,9 @@ class GraphLayer(nn.Module):
         if _truthy(cfg.get("use_layer_norm")):
             self.layers.append(LayerNorm(self.output_dim, mode=cfg.get("layer_norm_mode") or "graph"))
 
-    def forward(self, X, edge_index, attention_threshold=0.0, **kwargs):
+    def forward(self, X, edge_index, attention_threshold=0.0, rows_out=None, **kwargs):
+        """rows_out = n: the caller only uses nodes 0..n-1 of the result (the decoder: models.py:852 keeps the grid
+        rows).  Honoured when the last module is a GCNConv -- its aggregation then produces just those receivers."""
         if self.layer_type == "simple_conv":
             return self.layers(x=X, edge_index=edge_index)
         if self.layer_type == "sparse_gat":
@@ -129,8 +132,18 @@ class GraphLayer(nn.Module):
             fuse = isinstance(nxt, nn.PReLU)
             if type(m) is GCNConv:
                 g = GLOBAL_CACHE.get(edge_index, n, CSR_LOOPS)
-                h = ops.linear(X, m.lin.weight)
-                X = ops.aggregate(h, g, NORM_GCN, m.bias, nxt.weight if fuse else None)  # + bias + PReLU fused
+                W, b, C = m.lin.weight, m.bias, m.out_channels
+                if C % 4:
+                    # rows of 4k+r floats would force every kernel of this layer onto its scalar path: compute a
+                    # zero-padded 4-aligned layer (extra output channels are exactly 0) and slice the result
+                    W = F.pad(W, (0, 0, 0, 4 - C % 4))
+                    b = F.pad(b, (0, 4 - C % 4)) if b is not None else None
+                last = i + (2 if fuse else 1) >= len(mods)
+                h = ops.linear(X, W)
+                X = ops.aggregate(h, g, NORM_GCN, b, nxt.weight if fuse else None,     # + bias + PReLU fused
+                                  rows_out if last else None)
+                if C % 4:
+                    X = X[..., :C]
                 i += 2 if fuse else 1
             elif type(m) is GATConv:
                 X = m(X, edge_index)
@@ -232,6 +245,6 @@ class WeatherPrediction(nn.Module):
         else:
             proc = self.processor(X=mesh_lat, edge_index=self.processing_graph,
                                   attention_threshold=attention_threshold)
-        dec = self.decoder(X=torch.cat((grid_lat, proc), dim=1), edge_index=self.decoding_graph)
+        dec = self.decoder(X=torch.cat((grid_lat, proc), dim=1), edge_index=self.decoding_graph, rows_out=G)
         out = dec[:, :G]
         return out.squeeze(0) if squeeze else out

@@ -85,7 +85,7 @@ def spmm_raw(rowptr, col, w, x3, n_out, bias=None, slope=None, want_z=False):
     with torch.cuda.device(x3.device):
         nnz = int(col.numel())
         nbytes = 4 * B * C * (n_in + n_out * (2 if want_z else 1)) + nnz * (8 if w is not None else 4) + 4 * (n_out + 1)
-        _call("gcl_spmm_f32", _p(rowptr), _p(col), _p(w), _p(x3), _p(out), B, n_out, C, n_in * C, n_out * C,
+        _call("gcl_spmm_f32", _p(rowptr), _p(col), _p(w), _p(x3), _p(out), B, n_out, n_in, C, n_in * C, n_out * C,
               _p(bias), _p(slope), _p(z), nnz, _stream(), nbytes=nbytes, tag=f"N{n_out}xC{C}xB{B}")
     return out, z
 
@@ -173,15 +173,18 @@ class _Aggregate(torch.autograd.Function):
     sender-grouped CSR (A_w^T), so it is a gather too -- no atomics."""
 
     @staticmethod
-    def forward(ctx, x, bias, slope, graph: CSRGraph, kind: int):
+    def forward(ctx, x, bias, slope, graph: CSRGraph, kind: int, rows_out=None):
         x3, squeeze = _as3(_chk(x, "x"))
         if x3.shape[1] != graph.num_nodes:
             raise ValueError(f"gcl_b200: x has {x3.shape[1]} nodes, graph has {graph.num_nodes}")
+        n_out = graph.num_nodes if rows_out is None else int(rows_out)   # receivers 0 .. n_out-1 only
+        if not 0 < n_out <= graph.num_nodes:
+            raise ValueError(f"gcl_b200: rows_out={rows_out} outside 1..{graph.num_nodes}")
         bias_c = _chk(bias, "bias") if bias is not None else None
         slope_c = _chk(slope, "slope") if slope is not None else None
         w, _ = graph.weights(kind)
         need_z = slope_c is not None and any(ctx.needs_input_grad[:3])
-        out, z = spmm_raw(graph.rowptr, graph.col, w, x3, graph.num_nodes, bias_c, slope_c, need_z)
+        out, z = spmm_raw(graph.rowptr, graph.col, w, x3, n_out, bias_c, slope_c, need_z)
         ctx.graph, ctx.kind, ctx.squeeze = graph, kind, squeeze
         ctx.has_bias, ctx.has_slope = bias is not None, slope is not None
         ctx.save_for_backward(z, slope_c)
@@ -208,11 +211,12 @@ class _Aggregate(torch.autograd.Function):
             dx, _ = spmm_raw(g.rowptr_t, g.col_t, wt, d3, g.num_nodes)
             if ctx.squeeze:
                 dx = dx.squeeze(0)
-        return dx, dbias, (dslope if ctx.has_slope and ctx.needs_input_grad[2] else None), None, None
+        return dx, dbias, (dslope if ctx.has_slope and ctx.needs_input_grad[2] else None), None, None, None
 
 
-def aggregate(x, graph: CSRGraph, kind: int, bias=None, prelu_slope=None):
-    return _Aggregate.apply(x, bias, prelu_slope, graph, kind)
+def aggregate(x, graph: CSRGraph, kind: int, bias=None, prelu_slope=None, rows_out=None):
+    """rows_out = n: only receivers 0..n-1 are produced ([.., n, C]); their gradient flows back to all senders."""
+    return _Aggregate.apply(x, bias, prelu_slope, graph, kind, rows_out)
 
 
 class _Linear(torch.autograd.Function):

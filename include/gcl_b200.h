@@ -97,9 +97,12 @@ int gcl_csr_weights(const int32_t* rowptr, const int32_t* col, const int32_t* pe
  *   epi: (+ bias[C]) then optional PReLU (slope = *prelu_slope, device scalar; models.py:316 shares
  *   one nn.PReLU per GraphLayer).  z_out (nullable) receives the value before PReLU.
  *   w nullable (= 1).  x and out must not alias.
+ *   n_rows_out may be a prefix of the CSR's rows (the decoder only needs its grid rows, models.py:852);
+ *   n_rows_in = rows x holds per sample: entries whose column is >= n_rows_in count as zero rows (the
+ *   backward of such a prefix-restricted call reads a [B, n_rows_in, C] gradient through the transposed CSR).
  */
 int gcl_spmm_f32(const int32_t* rowptr, const int32_t* col, const float* w, const float* x,
-                 float* out, int64_t batch, int64_t n_rows_out, int64_t channels, int64_t x_bstride,
+                 float* out, int64_t batch, int64_t n_rows_out, int64_t n_rows_in, int64_t channels, int64_t x_bstride,
                  int64_t out_bstride, const float* bias, const float* prelu_slope, float* z_out,
                  int64_t nnz /* number of CSR entries, 0 = unknown (scheduling hint only) */, void* stream);
 

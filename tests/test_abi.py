@@ -31,7 +31,7 @@ def test_version_and_error_string():
     lib = _cabi.load()
     assert lib.gcl_version() == _cabi.ABI_VERSION
     # a bad-argument call must return an error code and set the thread-local message (no CUDA needed)
-    rc = lib.gcl_spmm_f32(None, None, None, None, None, 1, 1, 4, 4, 4, None, None, None, 0, None)
+    rc = lib.gcl_spmm_f32(None, None, None, None, None, 1, 1, 1, 4, 4, 4, None, None, None, 0, None)
     assert rc == -1
     assert "null pointer" in _cabi.last_error()
     assert lib.gcl_csr_workspace_bytes(10, 5) > 0
