@@ -116,8 +116,15 @@ __device__ __forceinline__ float gmax(float v, unsigned mask) {
   return v;
 }
 
+// Hot-loop rules for the three aggregate kernels below (from the SASS of the first version, which spent ~85% of
+// its instructions on 64-bit address arithmetic, per-sample `s < nb` branches around every gather and spills):
+//   * a ragged last sample block re-reads sample nb - 1 instead of branching (only stores are guarded), idle
+//     lanes (C / VW < L) re-read word 0;
+//   * per-sample base pointers are formed once per (row, head); a gather is then base + (uint32) c * HC;
+//   * 2 CTAs / SM (128 registers) -- the gathers of SB samples x 2 unrolled neighbours give each lane 8 independent
+//     128-bit loads in flight, which covers the L2 latency without a third CTA.
 template <int VW, int L, int SB>
-__global__ void __launch_bounds__(kWarps * 32, 3)
+__global__ void __launch_bounds__(kWarps * 32, 2)
     gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                    const int32_t* __restrict__ perm, const float* __restrict__ z, const float* __restrict__ a_src,
                    const float* __restrict__ a_dst, const float* __restrict__ bias, float* __restrict__ out,
@@ -137,28 +144,38 @@ __global__ void __launch_bounds__(kWarps * 32, 3)
   const int words = (C + VW - 1) / VW, nchunks = (words + L - 1) / L;
   const float hscale = concat ? 1.f : 1.f / (float)H;     // head mean folded into the attention weight
   const bool single = (end - beg) <= L;                   // whole row in one pass of the group's lanes
+  int64_t srow[SB];                                       // first node row of (clamped) sample s
+#pragma unroll
+  for (int s = 0; s < SB; ++s) srow[s] = (int64_t)(b0 + min(s, nb - 1)) * N;
 
   for (int chunk = 0; chunk < nchunks; ++chunk) {
     const int off = (chunk * L + gl) * VW;
     const bool live = off < C;
+    const int offc = live ? off : 0;
     typename V::T acc[SB];
 #pragma unroll
     for (int s = 0; s < SB; ++s) acc[s] = V::zero();
     for (int h = 0; h < H; ++h) {
+      const float* zp[SB];                                 // z[b, 0, h, offc]
+      const float* asp[SB];                                // a_src[b, 0, h]
       float adi[SB], m[SB], rl[SB];
 #pragma unroll
-      for (int s = 0; s < SB; ++s) adi[s] = (s < nb) ? a_dst[((int64_t)(b0 + s) * N + i) * H + h] : 0.f;
+      for (int s = 0; s < SB; ++s) {
+        zp[s] = z + srow[s] * HC + h * C + offc;
+        asp[s] = a_src + srow[s] * H + h;
+        adi[s] = a_dst[(srow[s] + i) * H + h];
+      }
       float e_own[SB];                                     // single-pass rows: this lane's edge logit
       const int32_t k_own = beg + gl;
-      const int32_t c_own = (single && k_own < end) ? col[k_own] : 0;
+      const bool own = single && k_own < end;
+      const int32_t c_own = own ? col[k_own] : 0;
       if (single) {
         // lane k holds edge k: max and sum are two group reductions, one exp per edge
 #pragma unroll
         for (int s = 0; s < SB; ++s) {
-          e_own[s] = (s < nb && k_own < end) ? leaky(a_src[((int64_t)(b0 + s) * N + c_own) * H + h] + adi[s], slope)
-                                             : -INFINITY;
+          e_own[s] = own ? leaky(asp[s][(uint32_t)c_own * (uint32_t)H] + adi[s], slope) : -INFINITY;
           m[s] = gmax<L>(e_own[s], mask);
-          e_own[s] = (k_own < end && s < nb) ? __expf(e_own[s] - m[s]) : 0.f;
+          e_own[s] = own ? __expf(e_own[s] - m[s]) : 0.f;
           rl[s] = 1.f / (gsum<L>(e_own[s], mask) + 1e-16f);
         }
       } else {
@@ -166,15 +183,13 @@ __global__ void __launch_bounds__(kWarps * 32, 3)
 #pragma unroll
         for (int s = 0; s < SB; ++s) { m[s] = -INFINITY; l[s] = 0.f; }
         for (int32_t k = beg + gl; k < end; k += L) {        // online (max, sum) per sample over long rows
-          const int32_t c = col[k];
+          const uint32_t ch = (uint32_t)col[k] * (uint32_t)H;
 #pragma unroll
           for (int s = 0; s < SB; ++s) {
-            if (s < nb) {
-              const float e = leaky(a_src[((int64_t)(b0 + s) * N + c) * H + h] + adi[s], slope);
-              const float mn = fmaxf(m[s], e);
-              l[s] = l[s] * __expf(m[s] - mn) + __expf(e - mn);
-              m[s] = mn;
-            }
+            const float e = leaky(asp[s][ch] + adi[s], slope);
+            const float mn = fmaxf(m[s], e);
+            l[s] = l[s] * __expf(m[s] - mn) + __expf(e - mn);
+            m[s] = mn;
           }
         }
 #pragma unroll
@@ -196,40 +211,35 @@ __global__ void __launch_bounds__(kWarps * 32, 3)
           const int32_t pk = (alpha_pyg && chunk == 0) ? perm[k] : 0;
 #pragma unroll
           for (int s = 0; s < SB; ++s) {
-            if (s < nb) {
-              float p;
-              if (single) p = e_own[s];
-              else p = __expf(leaky(a_src[((int64_t)(b0 + s) * N + c_reg) * H + h] + adi[s], slope) - m[s]);
-              const float al = p * rl[s];
-              a_reg[s] = al * hscale;
-              if (chunk == 0) {
-                alpha_csr[((int64_t)(b0 + s) * nnz + k) * H + h] = al;
-                if (alpha_pyg) alpha_pyg[((int64_t)(b0 + s) * nnz + pk) * H + h] = al;
-              }
+            float p;
+            if (single) p = e_own[s];
+            else p = __expf(leaky(asp[s][(uint32_t)c_reg * (uint32_t)H] + adi[s], slope) - m[s]);
+            const float al = p * rl[s];
+            a_reg[s] = al * hscale;
+            if (chunk == 0 && s < nb) {
+              alpha_csr[((int64_t)(b0 + s) * nnz + k) * H + h] = al;
+              if (alpha_pyg) alpha_pyg[((int64_t)(b0 + s) * nnz + pk) * H + h] = al;
             }
           }
         }
 #pragma unroll 2
         for (int j = 0; j < n; ++j) {
-          const int32_t c = __shfl_sync(mask, c_reg, j, L);
+          const uint32_t ro = (uint32_t)__shfl_sync(mask, c_reg, j, L) * (uint32_t)HC;
           float a[SB];
+          typename V::T v[SB];
 #pragma unroll
-          for (int s = 0; s < SB; ++s) a[s] = __shfl_sync(mask, a_reg[s], j, L);
-          if (live) {
-            typename V::T v[SB];
-#pragma unroll
-            for (int s = 0; s < SB; ++s)
-              if (s < nb) v[s] = V::load(z + ((int64_t)(b0 + s) * N + c) * HC + h * C + off);
-#pragma unroll
-            for (int s = 0; s < SB; ++s)
-              if (s < nb) V::fma(acc[s], a[s], v[s]);
+          for (int s = 0; s < SB; ++s) {
+            a[s] = __shfl_sync(mask, a_reg[s], j, L);
+            v[s] = V::load(zp[s] + ro);
           }
+#pragma unroll
+          for (int s = 0; s < SB; ++s) V::fma(acc[s], a[s], v[s]);
         }
       }
-      if (concat && live) {
+      if (concat) {
 #pragma unroll
         for (int s = 0; s < SB; ++s) {
-          if (s < nb) {
+          if (live && s < nb) {
             typename V::T o = acc[s];
             if (bias) o = V::add(o, V::load(bias + h * C + off));
             V::store(out + ((int64_t)(b0 + s) * N + i) * Cout + h * C + off, o);
@@ -310,39 +320,46 @@ __global__ void __launch_bounds__(kWarps * 32, 2)
 
   for (int h = 0; h < H; ++h) {
     const float* dbase = dout + (concat ? h * C : 0);
+    const int gofs = gl * VW < C ? gl * VW : 0;             // idle lanes re-read word 0 (their products are dropped)
+    const bool glive = gl * VW < C;
     typename V::T dv[SB];
+    const float* zp[SB];                                    // z[b, 0, h, gofs], ragged sample blocks re-read nb - 1
 #pragma unroll
-    for (int s = 0; s < SB; ++s)
-      dv[s] = (one && s < nb && gl * VW < C) ? V::load(dbase + ((int64_t)(b0 + s) * N + i) * Cout + gl * VW) : V::zero();
+    for (int s = 0; s < SB; ++s) {
+      const int64_t sb = b0 + min(s, nb - 1);
+      zp[s] = z + sb * N * HC + h * C + gofs;
+      dv[s] = (one && glive) ? V::load(dbase + (sb * N + i) * Cout + gofs) : V::zero();
+    }
     // finished dalpha (scaled by the head-mean factor) of this lane's (edge, sample) in the batch starting at `base`
     auto batch = [&](int32_t base) -> float {
       float p[L];
+      if (one) {
+        typename V::T zv[NB][SB];
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const int32_t k = base + j;
-        const int32_t c = k < end ? col[k] : -1;
+        for (int j = 0; j < NB; ++j) {
+          const int32_t k = min(base + j, end - 1);          // past the row end: re-read the last edge, dropped below
+          const uint32_t ro = (uint32_t)col[k] * (uint32_t)HC;
 #pragma unroll
-        for (int s = 0; s < SB; ++s) p[j * SB + s] = 0.f;
-        if (c >= 0) {
-          if (one) {
-            if (gl * VW < C) {
-              typename V::T zv[SB];
+          for (int s = 0; s < SB; ++s) zv[j][s] = V::load(zp[s] + ro);
+        }
 #pragma unroll
-              for (int s = 0; s < SB; ++s)
-                if (s < nb) zv[s] = V::load(z + ((int64_t)(b0 + s) * N + c) * HC + h * C + gl * VW);
+        for (int j = 0; j < NB; ++j)
 #pragma unroll
-              for (int s = 0; s < SB; ++s)
-                if (s < nb) p[j * SB + s] = V::dot(dv[s], zv[s]);
-            }
-          } else {
-            for (int chunk = 0; chunk < nchunks; ++chunk) {
-              const int off = (chunk * L + gl) * VW;
-              if (off < C) {
+          for (int s = 0; s < SB; ++s) p[j * SB + s] = V::dot(dv[s], zv[j][s]);
+      } else {
 #pragma unroll
-                for (int s = 0; s < SB; ++s)
-                  if (s < nb)
-                    p[j * SB + s] += V::dot(V::load(dbase + ((int64_t)(b0 + s) * N + i) * Cout + off),
-                                            V::load(z + ((int64_t)(b0 + s) * N + c) * HC + h * C + off));
+        for (int j = 0; j < NB; ++j) {
+          const int32_t k = min(base + j, end - 1);
+          const uint32_t ro = (uint32_t)col[k] * (uint32_t)HC;
+#pragma unroll
+          for (int s = 0; s < SB; ++s) p[j * SB + s] = 0.f;
+          for (int chunk = 0; chunk < nchunks; ++chunk) {
+            const int off = (chunk * L + gl) * VW;
+            if (off < C) {
+#pragma unroll
+              for (int s = 0; s < SB; ++s) {
+                const int64_t sb = b0 + min(s, nb - 1);
+                p[j * SB + s] += V::dot(V::load(dbase + (sb * N + i) * Cout + off), V::load(zp[s] - gofs + off + ro));
               }
             }
           }
@@ -410,7 +427,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2)
 // Backward pass 2, group per (sender j, SB samples), sender-grouped CSR:
 //   da_src[b,j,h] = sum_k g_k ;  dz[b,j,h,:] = sum_k alpha_k do_h(i_k) + da_src att_src[h] + da_dst att_dst[h]
 template <int VW, int L, int SB>
-__global__ void __launch_bounds__(kWarps * 32, 3)
+__global__ void __launch_bounds__(kWarps * 32, 2)
     gat_bwd_src_kernel(const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
                        const int32_t* __restrict__ t2r, const float* __restrict__ alpha_csr,
                        const float* __restrict__ g_csr, const float* __restrict__ att_src,
@@ -430,30 +447,40 @@ __global__ void __launch_bounds__(kWarps * 32, 3)
   const int HC = H * C, Cout = concat ? HC : C;
   const int words = (C + VW - 1) / VW, nchunks = (words + L - 1) / L;
   const float hs = concat ? 1.f : 1.f / (float)H;
+  int64_t sb_[SB];                                          // (clamped) sample index
+#pragma unroll
+  for (int s = 0; s < SB; ++s) sb_[s] = b0 + min(s, nb - 1);
 
   for (int h = 0; h < H; ++h) {
+    const float* gp[SB];                                    // g_csr[b, 0, h], alpha_csr[b, 0, h]
+    const float* ap[SB];
+#pragma unroll
+    for (int s = 0; s < SB; ++s) {
+      gp[s] = g_csr + sb_[s] * nnz * H + h;
+      ap[s] = alpha_csr + sb_[s] * nnz * H + h;
+    }
     float gsv[SB];
 #pragma unroll
     for (int s = 0; s < SB; ++s) gsv[s] = 0.f;
     for (int32_t k = beg + gl; k < end; k += L) {
-      const int32_t kr = t2r[k];
+      const uint32_t kr = (uint32_t)t2r[k] * (uint32_t)H;
 #pragma unroll
-      for (int s = 0; s < SB; ++s)
-        if (s < nb) gsv[s] += g_csr[((int64_t)(b0 + s) * nnz + kr) * H + h];
+      for (int s = 0; s < SB; ++s) gsv[s] += gp[s][kr];
     }
     float dad[SB];
 #pragma unroll
     for (int s = 0; s < SB; ++s) {
       gsv[s] = gsum<L>(gsv[s], mask);
-      dad[s] = 0.f;
-      if (s < nb) {
-        dad[s] = da_dst[((int64_t)(b0 + s) * N + jn) * H + h];
-        if (gl == 0) da_src[((int64_t)(b0 + s) * N + jn) * H + h] = gsv[s];
-      }
+      dad[s] = da_dst[(sb_[s] * N + jn) * H + h];
+      if (gl == 0 && s < nb) da_src[(sb_[s] * N + jn) * H + h] = gsv[s];
     }
     for (int chunk = 0; chunk < nchunks; ++chunk) {
       const int off = (chunk * L + gl) * VW;
       const bool live = off < C;
+      const int offc = live ? off : 0;
+      const float* dp[SB];                                  // dout[b, 0, (h), offc]
+#pragma unroll
+      for (int s = 0; s < SB; ++s) dp[s] = dout + sb_[s] * N * Cout + (concat ? h * C : 0) + offc;
       typename V::T acc[SB];
 #pragma unroll
       for (int s = 0; s < SB; ++s) acc[s] = V::zero();
@@ -466,26 +493,22 @@ __global__ void __launch_bounds__(kWarps * 32, 3)
         for (int s = 0; s < SB; ++s) a_reg[s] = 0.f;
         if (k < end) {
           i_reg = col_t[k];
-          const int32_t kr = t2r[k];
+          const uint32_t kr = (uint32_t)t2r[k] * (uint32_t)H;
 #pragma unroll
-          for (int s = 0; s < SB; ++s)
-            if (s < nb) a_reg[s] = alpha_csr[((int64_t)(b0 + s) * nnz + kr) * H + h] * hs;
+          for (int s = 0; s < SB; ++s) a_reg[s] = ap[s][kr] * hs;
         }
 #pragma unroll 2
         for (int e = 0; e < n; ++e) {
-          const int32_t ii = __shfl_sync(mask, i_reg, e, L);
+          const uint32_t ro = (uint32_t)__shfl_sync(mask, i_reg, e, L) * (uint32_t)Cout;
           float a[SB];
+          typename V::T v[SB];
 #pragma unroll
-          for (int s = 0; s < SB; ++s) a[s] = __shfl_sync(mask, a_reg[s], e, L);
-          if (live) {
-            typename V::T v[SB];
-#pragma unroll
-            for (int s = 0; s < SB; ++s)
-              if (s < nb) v[s] = V::load(dout + ((int64_t)(b0 + s) * N + ii) * Cout + (concat ? h * C : 0) + off);
-#pragma unroll
-            for (int s = 0; s < SB; ++s)
-              if (s < nb) V::fma(acc[s], a[s], v[s]);
+          for (int s = 0; s < SB; ++s) {
+            a[s] = __shfl_sync(mask, a_reg[s], e, L);
+            v[s] = V::load(dp[s] + ro);
           }
+#pragma unroll
+          for (int s = 0; s < SB; ++s) V::fma(acc[s], a[s], v[s]);
         }
       }
       if (live) {
@@ -681,6 +704,8 @@ extern "C" int gcl_gat_fwd_f32(const int32_t* rowptr, const int32_t* col, const 
                                int64_t heads, int64_t c, int concat, float negative_slope, void* stream) {
   GCL_CHECK_ARG(rowptr && col && z && a_src && a_dst && out && alpha_csr, "gcl_gat_fwd_f32: null pointer argument");
   GCL_CHECK_ARG(!alpha_pyg || perm, "gcl_gat_fwd_f32: alpha_pyg needs perm");
+  GCL_CHECK_ARG(n_nodes * heads * c < (1ll << 31) && nnz * heads < (1ll << 31),
+                "gcl_gat_fwd_f32: one sample's features / attention entries must index with 31 bits");
   GCL_CHECK_ARG(batch >= 0 && batch <= 65535 && n_nodes >= 0 && nnz >= 0 && heads > 0 && c > 0,
                 "gcl_gat_fwd_f32: bad sizes");
   if (batch == 0 || n_nodes == 0) return GCL_OK;
@@ -704,6 +729,8 @@ extern "C" int gcl_gat_bwd_f32(const int32_t* rowptr, const int32_t* col, const 
   GCL_CHECK_ARG(rowptr && col && rowptr_t && col_t && t2r && z && a_src && a_dst && alpha_csr && att_src && att_dst &&
                     dout && g_csr && da_src && da_dst && dz,
                 "gcl_gat_bwd_f32: null pointer argument");
+  GCL_CHECK_ARG(n_nodes * heads * c < (1ll << 31) && nnz * heads < (1ll << 31),
+                "gcl_gat_bwd_f32: one sample's features / attention entries must index with 31 bits");
   GCL_CHECK_ARG(batch >= 0 && batch <= 65535 && n_nodes >= 0 && nnz >= 0 && heads > 0 && c > 0,
                 "gcl_gat_bwd_f32: bad sizes");
   if (batch == 0 || n_nodes == 0) return GCL_OK;
