@@ -221,22 +221,23 @@ __global__ void __launch_bounds__(kThreads, 2)
   }
 }
 
-// out[i] = sum_s part[s * n + i] in a fixed order: 8 interleaved partial sums over s (one per threadIdx.y),
-// then those 8 in ascending order.  Block (32, 8) per 32 outputs, so even a 64 x 64 dW is spread over 128 CTAs
+// out[i] = sum_s part[s * n + i] in a fixed order: 32 interleaved partial sums over s (one per threadIdx.y),
+// then those 32 in ascending order.  Block (32, 32) per 32 outputs, so even a 64 x 64 dW is spread over 128 CTAs
 // (one thread per output summing 148 slices serially took 12-15 us per call, launch-latency sized work).
 __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n,
                                        int nsplit) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[32][33];
   const int64_t i = blockIdx.x * 32ll + threadIdx.x;
   float s = 0.f;
   if (i < n)
-    for (int k = threadIdx.y; k < nsplit; k += 8) s += part[(int64_t)k * n + i];
+#pragma unroll 4
+    for (int k = threadIdx.y; k < nsplit; k += 32) s += part[(int64_t)k * n + i];
   sm[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && i < n) {
     float t = sm[0][threadIdx.x];
 #pragma unroll
-    for (int y = 1; y < 8; ++y) t += sm[y][threadIdx.x];
+    for (int y = 1; y < 32; ++y) t += sm[y][threadIdx.x];
     out[i] = t;
   }
 }
@@ -487,10 +488,10 @@ extern "C" int gcl_linear_bwd_dw_f32(const float* dy, const float* x, float* dW,
       float* upcs = part + (size_t)us * M * N;
       const int rc = umma_dw(dy, x, part, dbias ? upcs : nullptr, rows, M, N, s);
       if (rc != GCL_OK) return rc;
-      reduce_partials_kernel<<<(unsigned)ceil_div((int64_t)M * N, 32), dim3(32, 8), 0, s>>>(part, dW, (int64_t)M * N, us);
+      reduce_partials_kernel<<<(unsigned)ceil_div((int64_t)M * N, 32), dim3(32, 32), 0, s>>>(part, dW, (int64_t)M * N, us);
       GCL_CHECK_LAUNCH("gcl_linear_bwd_dw_f32(reduce)");
       if (dbias) {
-        reduce_partials_kernel<<<(unsigned)ceil_div(M, 32), dim3(32, 8), 0, s>>>(upcs, dbias, M, us);
+        reduce_partials_kernel<<<(unsigned)ceil_div(M, 32), dim3(32, 32), 0, s>>>(upcs, dbias, M, us);
         GCL_CHECK_LAUNCH("gcl_linear_bwd_dw_f32(reduce bias)");
       }
       return GCL_OK;
@@ -503,10 +504,10 @@ extern "C" int gcl_linear_bwd_dw_f32(const float* dy, const float* x, float* dW,
   else if (tm == 4) launch_tn_m<4>(tn, dy, x, part, dbias ? pcs : nullptr, rows, M, N, pl, s);
   else launch_tn_m<2>(tn, dy, x, part, dbias ? pcs : nullptr, rows, M, N, pl, s);
   GCL_CHECK_LAUNCH("gcl_linear_bwd_dw_f32(gemm_tn)");
-  reduce_partials_kernel<<<(unsigned)ceil_div((int64_t)M * N, 32), dim3(32, 8), 0, s>>>(part, dW, (int64_t)M * N, pl.nsplit);
+  reduce_partials_kernel<<<(unsigned)ceil_div((int64_t)M * N, 32), dim3(32, 32), 0, s>>>(part, dW, (int64_t)M * N, pl.nsplit);
   GCL_CHECK_LAUNCH("gcl_linear_bwd_dw_f32(reduce)");
   if (dbias) {
-    reduce_partials_kernel<<<(unsigned)ceil_div(M, 32), dim3(32, 8), 0, s>>>(pcs, dbias, M, pl.nsplit);
+    reduce_partials_kernel<<<(unsigned)ceil_div(M, 32), dim3(32, 32), 0, s>>>(pcs, dbias, M, pl.nsplit);
     GCL_CHECK_LAUNCH("gcl_linear_bwd_dw_f32(reduce bias)");
   }
   return GCL_OK;
@@ -538,7 +539,7 @@ extern "C" int gcl_colsum_f32(const float* x, float* out, int64_t rows, int64_t 
   else
     colsum_partial_kernel<<<pl.nblk, dim3(32, 8), 0, s>>>(x, part, rows, (int)cols, pl.rows_per_block);
   GCL_CHECK_LAUNCH("gcl_colsum_f32(partial)");
-  reduce_partials_kernel<<<(unsigned)ceil_div(cols, 32), dim3(32, 8), 0, s>>>(part, out, cols, pl.nblk);
+  reduce_partials_kernel<<<(unsigned)ceil_div(cols, 32), dim3(32, 32), 0, s>>>(part, out, cols, pl.nblk);
   GCL_CHECK_LAUNCH("gcl_colsum_f32(reduce)");
   return GCL_OK;
 }

@@ -13,8 +13,13 @@
 #include "common.cuh"
 #include "scan.cuh"
 
+#ifndef GCL_GAT_UNROLL
+#define GCL_GAT_UNROLL 2
+#endif
 namespace gcl {
 namespace {
+constexpr int kGatUnroll = GCL_GAT_UNROLL;   // neighbours whose gathers are issued back to back
+
 
 constexpr int kWarps = 8;
 
@@ -124,7 +129,7 @@ __device__ __forceinline__ float gmax(float v, unsigned mask) {
 //   * 2 CTAs / SM (128 registers) -- the gathers of SB samples x 2 unrolled neighbours give each lane 8 independent
 //     128-bit loads in flight, which covers the L2 latency without a third CTA.
 template <int VW, int L, int SB>
-__global__ void __launch_bounds__(kWarps * 32, 2)
+__global__ void __launch_bounds__(kWarps * 32, SB >= 4 ? 2 : 4)
     gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                    const int32_t* __restrict__ perm, const float* __restrict__ z, const float* __restrict__ a_src,
                    const float* __restrict__ a_dst, const float* __restrict__ bias, float* __restrict__ out,
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2)
             }
           }
         }
-#pragma unroll 2
+#pragma unroll kGatUnroll
         for (int j = 0; j < n; ++j) {
           const uint32_t ro = (uint32_t)__shfl_sync(mask, c_reg, j, L) * (uint32_t)HC;
           float a[SB];
@@ -261,6 +266,36 @@ __global__ void __launch_bounds__(kWarps * 32, 2)
   }
 }
 
+// Attention coefficients alone, one thread per (sample, receiver, head): alpha = softmax_k LeakyReLU(a_src[col_k] +
+// a_dst[i]).  With the coefficients in memory (the backward needs them there anyway) the single-head aggregation
+// IS the SpMM kernel with per-sample weights: no exp, no reductions and a third of the instructions on the
+// gather path (the fused kernel above spends ~70% of its instructions outside the gathers).
+__global__ void __launch_bounds__(256)
+    gat_alpha_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                     const int32_t* __restrict__ perm, const float* __restrict__ a_src, const float* __restrict__ a_dst,
+                     float* __restrict__ alpha_csr, float* __restrict__ alpha_pyg, int64_t N, int64_t nnz, int B, int H,
+                     float slope) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;     // ((b * N) + i) * H + h, i.e. the a_dst index
+  if (t >= (int64_t)B * N * H) return;
+  const int h = (int)(t % H);
+  const int64_t bi = t / H, i = bi % N, b = bi / N;
+  const int32_t beg = rowptr[i], end = rowptr[i + 1];
+  const float adi = a_dst[t];
+  const float* as = a_src + b * N * H + h;
+  float m = -INFINITY;
+  for (int32_t k = beg; k < end; ++k) m = fmaxf(m, leaky(as[(uint32_t)col[k] * (uint32_t)H] + adi, slope));
+  float l = 0.f;
+  for (int32_t k = beg; k < end; ++k) l += __expf(leaky(as[(uint32_t)col[k] * (uint32_t)H] + adi, slope) - m);
+  const float rl = 1.f / (l + 1e-16f);
+  float* ac = alpha_csr + b * nnz * H + h;
+  float* ap = alpha_pyg ? alpha_pyg + b * nnz * H + h : nullptr;
+  for (int32_t k = beg; k < end; ++k) {
+    const float al = __expf(leaky(as[(uint32_t)col[k] * (uint32_t)H] + adi, slope) - m) * rl;
+    ac[(int64_t)k * H] = al;
+    if (ap) ap[(int64_t)perm[k] * H] = al;
+  }
+}
+
 // Butterfly transpose-reduce: every lane of an L-lane group holds L partial values p[0..L); afterwards lane g
 // holds the sum over the group's lanes of p[g].  L - 1 shuffles for L reductions (a shuffle tree per value would
 // be L log2 L).
@@ -293,7 +328,7 @@ __device__ __forceinline__ float gsum_strided(float v, unsigned mask) {
 // samples) of a batch are transpose-reduced at once, which leaves lane l with the finished dalpha of
 // (neighbour l / SB, sample l % SB); everything after that is per-lane scalar work on its own (edge, sample).
 template <int VW, int L, int SB>
-__global__ void __launch_bounds__(kWarps * 32, 2)
+__global__ void __launch_bounds__(kWarps * 32, SB >= 4 ? 2 : 4)
     gat_bwd_dst_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const float* __restrict__ z, const float* __restrict__ a_src,
                        const float* __restrict__ a_dst, const float* __restrict__ alpha_csr,
@@ -427,7 +462,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2)
 // Backward pass 2, group per (sender j, SB samples), sender-grouped CSR:
 //   da_src[b,j,h] = sum_k g_k ;  dz[b,j,h,:] = sum_k alpha_k do_h(i_k) + da_src att_src[h] + da_dst att_dst[h]
 template <int VW, int L, int SB>
-__global__ void __launch_bounds__(kWarps * 32, 2)
+__global__ void __launch_bounds__(kWarps * 32, SB >= 4 ? 2 : 4)
     gat_bwd_src_kernel(const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
                        const int32_t* __restrict__ t2r, const float* __restrict__ alpha_csr,
                        const float* __restrict__ g_csr, const float* __restrict__ att_src,
@@ -497,7 +532,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2)
 #pragma unroll
           for (int s = 0; s < SB; ++s) a_reg[s] = ap[s][kr] * hs;
         }
-#pragma unroll 2
+#pragma unroll kGatUnroll
         for (int e = 0; e < n; ++e) {
           const uint32_t ro = (uint32_t)__shfl_sync(mask, i_reg, e, L) * (uint32_t)Cout;
           float a[SB];
@@ -603,20 +638,21 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// out[i] = sum_k part[k * 2n + i], fixed order (8 interleaved partial sums, then ascending); block (32, 8)
+// out[i] = sum_k part[k * 2n + i], fixed order (32 interleaved partial sums, then ascending); block (32, 32)
 __global__ void reduce2_kernel(const float* __restrict__ part, int nblk, int n, float* __restrict__ out0,
                                float* __restrict__ out1) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[32][33];
   const int i = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
   if (i < 2 * n)
-    for (int k = threadIdx.y; k < nblk; k += 8) s += part[(int64_t)k * 2 * n + i];
+#pragma unroll 4
+    for (int k = threadIdx.y; k < nblk; k += 32) s += part[(int64_t)k * 2 * n + i];
   sm[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && i < 2 * n) {
     float t = sm[0][threadIdx.x];
 #pragma unroll
-    for (int y = 1; y < 8; ++y) t += sm[y][threadIdx.x];
+    for (int y = 1; y < 32; ++y) t += sm[y][threadIdx.x];
     if (i < n) out0[i] = t;
     else out1[i - n] = t;
   }
@@ -659,6 +695,12 @@ inline int pick_l(int words) { return words <= 4 ? 4 : words <= 8 ? 8 : words <=
 }  // namespace
 }  // namespace gcl
 
+namespace gcl {
+int spmm_run(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, float* out, int64_t batch,
+             int64_t n_rows_out, int64_t n_rows_in, int64_t channels, int64_t x_bstride, int64_t out_bstride,
+             const float* bias, const float* prelu_slope, float* z_out, int64_t nnz, int64_t w_bstride, float w_scale,
+             cudaStream_t s);
+}
 using namespace gcl;
 
 #define GAT_DISPATCH_L(VWC, SBC, LV, KERNEL, ...)                                        \
@@ -682,7 +724,8 @@ using namespace gcl;
 // samples per lane group (the scalar VW = 1 fallback keeps one)
 static int gat_pick_sb(int vw, int64_t B, int64_t N, int64_t HC) {
   if (vw != 4) return 1;
-  int sb = 4;
+  static const int cap = getenv("GCL_GAT_SB") ? atoi(getenv("GCL_GAT_SB")) : 4;
+  int sb = cap;
   while (sb > 1 && (sb > B || sb * N * HC * 4 > (48ll << 20))) sb >>= 1;
   return sb;
 }
@@ -710,6 +753,16 @@ extern "C" int gcl_gat_fwd_f32(const int32_t* rowptr, const int32_t* col, const 
                 "gcl_gat_fwd_f32: bad sizes");
   if (batch == 0 || n_nodes == 0) return GCL_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static const bool fused_only = getenv("GCL_GAT_FUSED") && getenv("GCL_GAT_FUSED")[0] == '1';
+  if (heads == 1 && !fused_only) {
+    // single head: coefficients by gat_alpha_kernel, aggregation = SpMM with per-sample weights
+    gat_alpha_kernel<<<(unsigned)ceil_div(batch * n_nodes, 256), 256, 0, s>>>(rowptr, col, perm, a_src, a_dst, alpha_csr,
+                                                                              alpha_pyg, n_nodes, nnz, (int)batch, 1,
+                                                                              negative_slope);
+    GCL_CHECK_LAUNCH("gcl_gat_fwd_f32(alpha)");
+    return spmm_run(rowptr, col, alpha_csr, z, out, batch, n_nodes, n_nodes, c, n_nodes * c, n_nodes * c, bias, nullptr,
+                    nullptr, nnz, nnz, 1.f, s);
+  }
   const int vw = (c % 4 == 0 && al16(z) && al16(out) && (!bias || al16(bias))) ? 4 : 1;
   const int l = pick_l((int)ceil_div(c, vw));
   const int sb = gat_pick_sb(vw, batch, n_nodes, heads * c);
@@ -778,7 +831,7 @@ extern "C" int gcl_gat_datt_f32(const float* z, const float* da_src, const float
     gat_datt_partial_kernel<<<pl.nblk, dim3(32, 8), 0, s>>>(z, da_src, da_dst, part, rows, (int)heads, (int)c,
                                                             pl.rows_per_block);
   GCL_CHECK_LAUNCH("gcl_gat_datt_f32(partial)");
-  reduce2_kernel<<<(unsigned)ceil_div(2 * HC, 32), dim3(32, 8), 0, s>>>(part, pl.nblk, HC, datt_src, datt_dst);
+  reduce2_kernel<<<(unsigned)ceil_div(2 * HC, 32), dim3(32, 32), 0, s>>>(part, pl.nblk, HC, datt_src, datt_dst);
   GCL_CHECK_LAUNCH("gcl_gat_datt_f32(reduce)");
   return GCL_OK;
 }

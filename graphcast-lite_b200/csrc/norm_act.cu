@@ -153,12 +153,21 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__global__ void sum_partials_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
-  // one warp, fixed order: lane-strided partial sums then a shuffle tree
+__global__ void __launch_bounds__(1024) sum_partials_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
+  // one block, fixed order: thread-strided partial sums, a shuffle tree per warp, then the 32 warp sums in order
+  __shared__ float ws[32];
   float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += 32) s += part[i];
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n; i += 1024) s += part[i];
   s = warp_sum(s);
-  if (threadIdx.x == 0) *out = s;
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += ws[k];
+    *out = t;
+  }
 }
 
 // ---- LayerNorm over the last dim, one warp per row, row cached in registers (C <= 32 * NPER) -------
@@ -379,21 +388,22 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// out[i] = sum_k part[k * n + i] in a fixed order (8 interleaved partial sums, then those 8 ascending); block
-// (32, 8) per 32 outputs.  Columns < C go to out0, the rest to out1.
+// out[i] = sum_k part[k * n + i] in a fixed order (32 interleaved partial sums, then those 32 ascending); block
+// (32, 32) per 32 outputs.  Columns < C go to out0, the rest to out1.
 __global__ void reduce_cols_kernel(const float* __restrict__ part, int nblk, int n, float* __restrict__ out0,
                                    float* __restrict__ out1, int C) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[32][33];
   const int i = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
   if (i < n)
-    for (int k = threadIdx.y; k < nblk; k += 8) s += part[(int64_t)k * n + i];
+#pragma unroll 4
+    for (int k = threadIdx.y; k < nblk; k += 32) s += part[(int64_t)k * n + i];
   sm[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && i < n) {
     float t = sm[0][threadIdx.x];
 #pragma unroll
-    for (int y = 1; y < 8; ++y) t += sm[y][threadIdx.x];
+    for (int y = 1; y < 32; ++y) t += sm[y][threadIdx.x];
     if (i < C) out0[i] = t;
     else out1[i - C] = t;
   }
@@ -452,7 +462,7 @@ extern "C" int gcl_prelu_bwd_f32(const float* dy, const float* x, const float* s
   float* part = static_cast<float*>(workspace);
   prelu_bwd_kernel<<<nblk, kEwThreads, 0, s>>>(dy, x, slope, dx, part, n, per_block);
   GCL_CHECK_LAUNCH("gcl_prelu_bwd_f32");
-  sum_partials_kernel<<<1, 32, 0, s>>>(part, nblk, dslope);
+  sum_partials_kernel<<<1, 1024, 0, s>>>(part, nblk, dslope);
   GCL_CHECK_LAUNCH("gcl_prelu_bwd_f32(reduce)");
   return GCL_OK;
 }
@@ -488,7 +498,7 @@ extern "C" int gcl_prelu_bwd_colsum_f32(const float* dy, const float* x, const f
   else
     prelu_bwd_colsum_kernel<<<pl.nblk, dim3(32, 8), 0, s>>>(dy, x, slope, dx, part, rows, (int)c, pl.rows_per_block);
   GCL_CHECK_LAUNCH("gcl_prelu_bwd_colsum_f32");
-  reduce_cols_kernel<<<(unsigned)ceil_div(c + 1, 32), dim3(32, 8), 0, s>>>(part, pl.nblk, (int)c + 1, dbias, dslope, (int)c);
+  reduce_cols_kernel<<<(unsigned)ceil_div(c + 1, 32), dim3(32, 32), 0, s>>>(part, pl.nblk, (int)c + 1, dbias, dslope, (int)c);
   GCL_CHECK_LAUNCH("gcl_prelu_bwd_colsum_f32(reduce)");
   return GCL_OK;
 }
@@ -578,7 +588,7 @@ extern "C" int gcl_layernorm_bwd_f32(const float* dy, const float* x, const floa
   }
   GCL_CHECK_LAUNCH("gcl_layernorm_bwd_f32");
   if (want_params) {
-    reduce_cols_kernel<<<(unsigned)ceil_div(2 * c, 32), dim3(32, 8), 0, s>>>(part, pl.nblk, 2 * C, dgamma, dbeta, C);
+    reduce_cols_kernel<<<(unsigned)ceil_div(2 * c, 32), dim3(32, 32), 0, s>>>(part, pl.nblk, 2 * C, dgamma, dbeta, C);
     GCL_CHECK_LAUNCH("gcl_layernorm_bwd_f32(reduce)");
   }
   return GCL_OK;

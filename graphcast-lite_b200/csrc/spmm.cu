@@ -46,13 +46,15 @@ constexpr int kWarpsPerBlock = 8;
 
 // SB samples of the same row per lane group: the row's (col, w) pairs are fetched once and every edge
 // issues SB independent 128-bit gathers (one per sample), which is what hides the L2/HBM latency.
-template <int VW, int L, int SB>
+// PW: per-sample weights w[b][k] (w_bstride floats apart) times w_scale -- the attention coefficients of GATConv;
+// otherwise one weight per CSR entry shared by all samples (GCN / mean).
+template <int VW, int L, int SB, bool PW>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                 const float* __restrict__ w, const float* __restrict__ x, float* __restrict__ out,
                 int64_t n_rows, int64_t n_in, int C, int nchunks, int64_t x_bstride, int64_t out_bstride, int B,
                 const float* __restrict__ bias, const float* __restrict__ prelu_slope,
-                float* __restrict__ z_out) {
+                float* __restrict__ z_out, int64_t w_bstride, float w_scale) {
   using V = Vec<VW>;
   constexpr int kGroups = 32 / L;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -75,19 +77,30 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   for (int32_t base = beg; base < end; base += L) {
     const int n = min(L, end - base);
     int32_t c_reg = 0;
-    float w_reg = 0.f;
+    float w_reg[PW ? SB : 1];
+#pragma unroll
+    for (int s = 0; s < (PW ? SB : 1); ++s) w_reg[s] = 0.f;
     if (gl < n) {
       c_reg = __ldg(col + base + gl);
-      w_reg = w ? __ldg(w + base + gl) : 1.f;
+      if (PW) {
+#pragma unroll
+        for (int s = 0; s < SB; ++s)
+          if (s < nb) w_reg[s] = w[(int64_t)(b0 + s) * w_bstride + base + gl] * w_scale;
+      } else {
+        w_reg[0] = w ? __ldg(w + base + gl) : 1.f;
+      }
       if (c_reg >= n_in) {   // entry points past the rows x holds (output restricted to a row prefix): a zero row
         c_reg = 0;
-        w_reg = 0.f;
+#pragma unroll
+        for (int s = 0; s < (PW ? SB : 1); ++s) w_reg[s] = 0.f;
       }
     }
 #pragma unroll 2
     for (int j = 0; j < n; ++j) {
       const int32_t c = __shfl_sync(mask, c_reg, j, L);
-      const float wt = __shfl_sync(mask, w_reg, j, L);
+      float wt[PW ? SB : 1];
+#pragma unroll
+      for (int s = 0; s < (PW ? SB : 1); ++s) wt[s] = __shfl_sync(mask, w_reg[s], j, L);
       if (live) {
         typename V::T v[SB];
 #pragma unroll
@@ -95,7 +108,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
           if (s < nb) v[s] = V::load(xb + (int64_t)s * x_bstride + (int64_t)c * C);
 #pragma unroll
         for (int s = 0; s < SB; ++s)
-          if (s < nb) V::fma(acc[s], wt, v[s]);
+          if (s < nb) V::fma(acc[s], wt[PW ? s : 0], v[s]);
       }
     }
   }
@@ -128,14 +141,20 @@ inline int pick_sb(int64_t B, int64_t n_rows, int64_t C, int64_t nnz) {
 template <int VW, int L, int SB>
 int launch(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, float* out, int64_t B,
            int64_t n_rows, int64_t n_in, int64_t C, int64_t xbs, int64_t obs, const float* bias, const float* slope,
-           float* z_out, cudaStream_t s) {
+           float* z_out, int64_t wbs, float wsc, cudaStream_t s) {
   const int64_t units = ceil_div(C, VW);          // vector words per row
   const int nchunks = (int)ceil_div(units, 32);
   const int64_t items = n_rows * nchunks;
   const int64_t per_block = (int64_t)kWarpsPerBlock * (32 / L);
   dim3 grid((unsigned)ceil_div(items, per_block), (unsigned)ceil_div(B, SB));
-  spmm_kernel<VW, L, SB><<<grid, kWarpsPerBlock * 32, 0, s>>>(rowptr, col, w, x, out, n_rows, n_in, (int)C, nchunks,
-                                                             xbs, obs, (int)B, bias, slope, z_out);
+  if (wbs > 0)
+    spmm_kernel<VW, L, SB, true><<<grid, kWarpsPerBlock * 32, 0, s>>>(rowptr, col, w, x, out, n_rows, n_in, (int)C,
+                                                                     nchunks, xbs, obs, (int)B, bias, slope, z_out, wbs,
+                                                                     wsc);
+  else
+    spmm_kernel<VW, L, SB, false><<<grid, kWarpsPerBlock * 32, 0, s>>>(rowptr, col, w, x, out, n_rows, n_in, (int)C,
+                                                                      nchunks, xbs, obs, (int)B, bias, slope, z_out, 0,
+                                                                      1.f);
   GCL_CHECK_LAUNCH("gcl_spmm_f32");
   return GCL_OK;
 }
@@ -143,25 +162,42 @@ int launch(const int32_t* rowptr, const int32_t* col, const float* w, const floa
 template <int VW, int L>
 int dispatch_sb(int sb, const int32_t* rowptr, const int32_t* col, const float* w, const float* x, float* out,
                 int64_t B, int64_t n_rows, int64_t n_in, int64_t C, int64_t xbs, int64_t obs, const float* bias,
-                const float* slope, float* z_out, cudaStream_t s) {
-  if (sb >= 8) return launch<VW, L, 8>(rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
-  if (sb >= 4) return launch<VW, L, 4>(rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
-  if (sb >= 2) return launch<VW, L, 2>(rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
-  return launch<VW, L, 1>(rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
+                const float* slope, float* z_out, int64_t wbs, float wsc, cudaStream_t s) {
+  if (sb >= 8) return launch<VW, L, 8>(rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, wbs, wsc, s);
+  if (sb >= 4) return launch<VW, L, 4>(rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, wbs, wsc, s);
+  if (sb >= 2) return launch<VW, L, 2>(rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, wbs, wsc, s);
+  return launch<VW, L, 1>(rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, wbs, wsc, s);
 }
 
 template <int VW>
 int dispatch_l(int64_t units, const int32_t* rowptr, const int32_t* col, const float* w, const float* x,
                float* out, int64_t B, int64_t n_rows, int64_t n_in, int64_t C, int64_t xbs, int64_t obs, const float* bias,
-               const float* slope, float* z_out, int64_t nnz, cudaStream_t s) {
-  const int sb = pick_sb(B, n_rows, C, nnz);
-  if (units <= 4) return dispatch_sb<VW, 4>(sb, rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
-  if (units <= 8) return dispatch_sb<VW, 8>(sb, rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
-  if (units <= 16) return dispatch_sb<VW, 16>(sb, rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
-  return dispatch_sb<VW, 32>(sb, rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, s);
+               const float* slope, float* z_out, int64_t nnz, int64_t wbs, float wsc, cudaStream_t s) {
+  int sb = pick_sb(B, n_rows, C, nnz);
+  static const int pw_cap = getenv("GCL_PW_SB") ? atoi(getenv("GCL_PW_SB")) : 4;
+  if (wbs > 0 && sb > pw_cap) sb = pw_cap;   // per-sample weights cost SB registers + shuffles per neighbour
+  if (units <= 4) return dispatch_sb<VW, 4>(sb, rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, wbs, wsc, s);
+  if (units <= 8) return dispatch_sb<VW, 8>(sb, rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, wbs, wsc, s);
+  if (units <= 16) return dispatch_sb<VW, 16>(sb, rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, wbs, wsc, s);
+  return dispatch_sb<VW, 32>(sb, rowptr, col, w, x, out, B, n_rows, n_in, C, xbs, obs, bias, slope, z_out, wbs, wsc, s);
 }
 
 }  // namespace
+
+// shared entry for gcl_spmm_f32 and the single-head GATConv aggregation (per-sample weights, w_bstride > 0)
+int spmm_run(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, float* out, int64_t batch,
+             int64_t n_rows_out, int64_t n_rows_in, int64_t channels, int64_t x_bstride, int64_t out_bstride,
+             const float* bias, const float* prelu_slope, float* z_out, int64_t nnz, int64_t w_bstride, float w_scale,
+             cudaStream_t s) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool vec = (channels % 4 == 0) && (x_bstride % 4 == 0) && (out_bstride % 4 == 0) && al16(x) && al16(out) &&
+                   (!bias || al16(bias)) && (!z_out || al16(z_out));
+  if (vec)
+    return dispatch_l<4>(channels / 4, rowptr, col, w, x, out, batch, n_rows_out, n_rows_in, channels, x_bstride,
+                         out_bstride, bias, prelu_slope, z_out, nnz, w_bstride, w_scale, s);
+  return dispatch_l<1>(channels, rowptr, col, w, x, out, batch, n_rows_out, n_rows_in, channels, x_bstride, out_bstride,
+                       bias, prelu_slope, z_out, nnz, w_bstride, w_scale, s);
+}
 }  // namespace gcl
 
 using namespace gcl;
@@ -178,13 +214,6 @@ extern "C" int gcl_spmm_f32(const int32_t* rowptr, const int32_t* col, const flo
   GCL_CHECK_ARG(n_rows_in > 0, "gcl_spmm_f32: n_rows_in must be positive");
   GCL_CHECK_ARG(batch <= 65535, "gcl_spmm_f32: batch %lld exceeds 65535", (long long)batch);
   if (batch == 0 || n_rows_out == 0) return GCL_OK;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  const bool vec = (channels % 4 == 0) && (x_bstride % 4 == 0) && (out_bstride % 4 == 0) && al16(x) && al16(out) &&
-                   (!bias || al16(bias)) && (!z_out || al16(z_out));
-  if (vec)
-    return dispatch_l<4>(channels / 4, rowptr, col, w, x, out, batch, n_rows_out, n_rows_in, channels, x_bstride,
-                         out_bstride, bias, prelu_slope, z_out, nnz, s);
-  return dispatch_l<1>(channels, rowptr, col, w, x, out, batch, n_rows_out, n_rows_in, channels, x_bstride, out_bstride,
-                       bias, prelu_slope, z_out, nnz, s);
+  return spmm_run(rowptr, col, w, x, out, batch, n_rows_out, n_rows_in, channels, x_bstride, out_bstride, bias,
+                  prelu_slope, z_out, nnz, 0, 1.f, static_cast<cudaStream_t>(stream));
 }
