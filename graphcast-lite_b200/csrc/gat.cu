@@ -743,7 +743,8 @@ extern "C" int gcl_gat_scores_f32(const float* z, const float* att_src, const fl
 
 extern "C" int gcl_gat_fwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* z,
                                const float* a_src, const float* a_dst, const float* bias, float* out,
-                               float* alpha_csr, float* alpha_pyg, int64_t batch, int64_t n_nodes, int64_t nnz,
+                               float* alpha_csr, float* alpha_pyg, const float* prelu_slope, float* z_out,
+                               int64_t batch, int64_t n_nodes, int64_t nnz,
                                int64_t heads, int64_t c, int concat, float negative_slope, void* stream) {
   GCL_CHECK_ARG(rowptr && col && z && a_src && a_dst && out && alpha_csr, "gcl_gat_fwd_f32: null pointer argument");
   GCL_CHECK_ARG(!alpha_pyg || perm, "gcl_gat_fwd_f32: alpha_pyg needs perm");
@@ -760,8 +761,12 @@ extern "C" int gcl_gat_fwd_f32(const int32_t* rowptr, const int32_t* col, const 
                                                                               alpha_pyg, n_nodes, nnz, (int)batch, 1,
                                                                               negative_slope);
     GCL_CHECK_LAUNCH("gcl_gat_fwd_f32(alpha)");
-    return spmm_run(rowptr, col, alpha_csr, z, out, batch, n_nodes, n_nodes, c, n_nodes * c, n_nodes * c, bias, nullptr,
-                    nullptr, nnz, nnz, 1.f, s);
+    return spmm_run(rowptr, col, alpha_csr, z, out, batch, n_nodes, n_nodes, c, n_nodes * c, n_nodes * c, bias,
+                    prelu_slope, z_out, nnz, nnz, 1.f, s);
+  }
+  if (prelu_slope) {
+    set_error("gcl_gat_fwd_f32: the fused PReLU epilogue exists for heads == 1 only");
+    return GCL_ERR_UNSUPPORTED;
   }
   const int vw = (c % 4 == 0 && al16(z) && al16(out) && (!bias || al16(bias))) ? 4 : 1;
   const int l = pick_l((int)ceil_div(c, vw));

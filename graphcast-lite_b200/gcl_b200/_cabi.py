@@ -38,7 +38,7 @@ _PROTOS = {
     "gcl_layernorm_bwd_workspace_bytes": (SZ, [I64, I64]),
     "gcl_layernorm_bwd_f32": (c_int, [P, P, P, P, P, P, P, P, I64, I64, P, SZ, P]),
     "gcl_gat_scores_f32": (c_int, [P, P, P, P, P, I64, I64, I64, P]),
-    "gcl_gat_fwd_f32": (c_int, [P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I32, F32, P]),
+    "gcl_gat_fwd_f32": (c_int, [P] * 12 + [I64, I64, I64, I64, I64, I32, F32, P]),
     "gcl_gat_bwd_f32": (c_int, [P] * 16 + [I64, I64, I64, I64, I64, I32, F32, P]),
     "gcl_gat_datt_workspace_bytes": (SZ, [I64, I64, I64]),
     "gcl_gat_datt_f32": (c_int, [P, P, P, P, P, I64, I64, I64, P, SZ, P]),

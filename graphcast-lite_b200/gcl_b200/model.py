@@ -146,8 +146,15 @@ class GraphLayer(nn.Module):
                     X = X[..., :C]
                 i += 2 if fuse else 1
             elif type(m) is GATConv:
-                X = m(X, edge_index)
-                i += 1
+                if fuse and m.heads == 1:                    # GATConv + the shared PReLU in one aggregation kernel
+                    g = GLOBAL_CACHE.get(edge_index, n, CSR_LOOPS if m.add_self_loops else CSR_RAW)
+                    z = ops.linear(X, m.lin.weight)
+                    X, _ = ops.gat_attend(z, m.att_src, m.att_dst, m.bias, g, 1, m.concat, m.negative_slope,
+                                          prelu_slope=nxt.weight)
+                    i += 2
+                else:
+                    X = m(X, edge_index)
+                    i += 1
             elif isinstance(m, nn.PReLU):
                 X = ops.prelu(X, m.weight)
                 i += 1

@@ -326,8 +326,11 @@ class _GAT(torch.autograd.Function):
     z is the already-transformed [B, N, H*C] (or [N, H*C]) feature matrix."""
 
     @staticmethod
-    def forward(ctx, z, att_src, att_dst, bias, graph: CSRGraph, heads, concat, slope, want_alpha):
+    def forward(ctx, z, att_src, att_dst, bias, graph: CSRGraph, heads, concat, slope, want_alpha, prelu_slope=None):
         z3, squeeze = _as3(_chk(z, "z"))
+        if prelu_slope is not None and int(heads) != 1:
+            raise NotImplementedError("gcl_b200: PReLU fused into GATConv needs heads == 1")
+        ps = _chk(prelu_slope, "prelu_slope") if prelu_slope is not None else None
         B, N, HC = z3.shape
         H = int(heads)
         C = HC // H
@@ -341,16 +344,18 @@ class _GAT(torch.autograd.Function):
         out = torch.empty((B, N, cout), dtype=torch.float32, device=dev)
         alpha = torch.empty((B, max(nnz, 1), H), dtype=torch.float32, device=dev)
         alpha_pyg = torch.empty((B, max(nnz, 1), H), dtype=torch.float32, device=dev) if want_alpha else None
+        zpre = torch.empty_like(out) if ps is not None else None
         with torch.cuda.device(dev):
             _call("gcl_gat_scores_f32", _p(z3), _p(a_s), _p(a_d), _p(asrc), _p(adst), B * N, H, C, _stream(),
                   nbytes=4 * B * N * (H * C + 2 * H), tag=f"R{B * N}xH{H}xC{C}")
             _call("gcl_gat_fwd_f32", _p(graph.rowptr), _p(graph.col), _p(graph.perm), _p(z3), _p(asrc), _p(adst),
-                  _p(bias_c), _p(out), _p(alpha), _p(alpha_pyg), B, N, nnz, H, C, int(bool(concat)), float(slope),
+                  _p(bias_c), _p(out), _p(alpha), _p(alpha_pyg), _p(ps), _p(zpre), B, N, nnz, H, C, int(bool(concat)),
+                  float(slope),
                   _stream(), nbytes=4 * B * (N * (H * C + cout + 2 * H) + nnz * H * (2 if want_alpha else 1)) + 4 * nnz
                   + 4 * (N + 1), tag=f"N{N}xH{H}xC{C}xB{B}")
         ctx.graph, ctx.H, ctx.C, ctx.concat, ctx.slope = graph, H, C, bool(concat), float(slope)
-        ctx.squeeze, ctx.has_bias = squeeze, bias is not None
-        ctx.save_for_backward(z3, asrc, adst, alpha, a_s, a_d)
+        ctx.squeeze, ctx.has_bias, ctx.has_prelu = squeeze, bias is not None, ps is not None
+        ctx.save_for_backward(z3, asrc, adst, alpha, a_s, a_d, zpre, ps)
         if squeeze:
             out = out.squeeze(0)
         if want_alpha:
@@ -361,11 +366,15 @@ class _GAT(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dalpha=None):
-        z3, asrc, adst, alpha, a_s, a_d = ctx.saved_tensors
+        z3, asrc, adst, alpha, a_s, a_d, zpre, ps = ctx.saved_tensors
         g = ctx.graph
         B, N, HC = z3.shape
         H, C = ctx.H, ctx.C
         d3, _ = _as3(_chk(dout, "grad_out"))
+        dslope = None
+        if ctx.has_prelu:
+            d3, dslope = prelu_bwd_raw(d3, zpre, ps)
+            dslope = dslope.view_as(ps)
         dev = z3.device
         gbuf = torch.empty_like(alpha)
         da_s = torch.empty_like(asrc)
@@ -387,11 +396,12 @@ class _GAT(torch.autograd.Function):
         dbias = colsum_raw(d3.view(-1, d3.shape[-1])) if ctx.has_bias else None
         if ctx.squeeze:
             dz = dz.squeeze(0)
-        return dz, datt_s.view(1, H, C), datt_d.view(1, H, C), dbias, None, None, None, None, None
+        return dz, datt_s.view(1, H, C), datt_d.view(1, H, C), dbias, None, None, None, None, None, dslope
 
 
-def gat_attend(z, att_src, att_dst, bias, graph, heads, concat, negative_slope, want_alpha=False):
-    return _GAT.apply(z, att_src, att_dst, bias, graph, heads, concat, negative_slope, want_alpha)
+def gat_attend(z, att_src, att_dst, bias, graph, heads, concat, negative_slope, want_alpha=False, prelu_slope=None):
+    """prelu_slope (heads == 1): PReLU applied behind the bias inside the aggregation kernel."""
+    return _GAT.apply(z, att_src, att_dst, bias, graph, heads, concat, negative_slope, want_alpha, prelu_slope)
 
 
 def edge_prune(ei_pyg: torch.Tensor, alpha_pyg: torch.Tensor, threshold: float) -> torch.Tensor:

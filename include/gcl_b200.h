@@ -178,7 +178,10 @@ int gcl_gat_scores_f32(const float* z, const float* att_src, const float* att_ds
                        float* a_dst, int64_t rows /* B*N */, int64_t heads, int64_t c, void* stream);
 int gcl_gat_fwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* z,
                     const float* a_src, const float* a_dst, const float* bias, float* out,
-                    float* alpha_csr, float* alpha_pyg, int64_t batch, int64_t n_nodes, int64_t nnz,
+                    float* alpha_csr, float* alpha_pyg,
+                    const float* prelu_slope /* nullable: PReLU fused behind the bias (models.py:316, 426-428) */,
+                    float* z_out /* nullable: the value before that PReLU; heads == 1 only */,
+                    int64_t batch, int64_t n_nodes, int64_t nnz,
                     int64_t heads, int64_t c, int concat, float negative_slope, void* stream);
 /* Backward.  Pass 1 (receiver-grouped): g = d(pre-LeakyReLU logit) per entry, da_dst.
  * Pass 2 (sender-grouped): dz = sum_i alpha_ij do_i + da_src att_src + da_dst att_dst, da_src.

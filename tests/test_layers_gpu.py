@@ -180,6 +180,44 @@ def test_gatconv_forward_backward_alpha(heads, concat, C, B):
     assert torch.allclose(s, torch.ones_like(s), atol=1e-5)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [None, 3])
+def test_gat_with_fused_prelu_matches_unfused(B):
+    """heads == 1: GATConv + PReLU in one aggregation kernel (the model's fused path) against GATConv then
+    PReLU of the oracle, forward and all gradients including the shared PReLU slope."""
+    import gcl_b200.nn as gnn
+    from gcl_b200 import ops
+    from gcl_b200.graph import CSR_LOOPS, GLOBAL_CACHE
+    onn = _oracle_nn()
+    n, cin, C = 500, 64, 64
+    ei = random_graph(n, 3000, seed=77, heavy=40, self_loops=5, dups=7, isolated=10)
+    torch.manual_seed(3)
+    ref = onn.GATConv(cin, C, heads=1, concat=False)
+    with torch.no_grad():
+        ref.bias.uniform_(-0.5, 0.5)
+    ref_act = torch.nn.PReLU()
+    mine = gnn.GATConv(cin, C, heads=1, concat=False).to(DEV)
+    _copy_params(mine, ref)
+    act = torch.nn.PReLU().to(DEV)
+    shape = (n, cin) if B is None else (B, n, cin)
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(8))
+    xg = x.to(DEV).requires_grad_(True)
+    xc = x.clone().requires_grad_(True)
+    g = GLOBAL_CACHE.get(ei.to(DEV), n, CSR_LOOPS)
+    z = ops.linear(xg, mine.lin.weight)
+    out_g, _ = ops.gat_attend(z, mine.att_src, mine.att_dst, mine.bias, g, 1, False, mine.negative_slope,
+                              prelu_slope=act.weight)
+    out_c = ref_act(ref(xc, ei))
+    assert_close(out_g, out_c, RTOL_F32, "GAT+PReLU out")
+    w = torch.randn(out_c.shape, generator=torch.Generator().manual_seed(9))
+    (out_g * w.to(DEV)).sum().backward()
+    (out_c * w).sum().backward()
+    assert_close(xg.grad, xc.grad, RTOL_F32, "dx")
+    assert_close(act.weight.grad, ref_act.weight.grad, RTOL_F32, "dslope")
+    for (k, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert_close(p.grad, q.grad, RTOL_F32, f"d{k}", atol=1e-6 if k == "att_dst" else 0.0)
+
+
 def test_sparse_gat_subclass_and_prune():
     """The reference's SparseGATConv (models.py:112-151) restated on top of OUR GATConv: subclassing,
     super().forward(..., return_attention_weights=True), threshold mask; plus the fused prune kernel."""
