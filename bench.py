@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--no-graph", action="store_true",
+                    help="eager launches instead of CUDA-graph replay (for ncu: it fails with LaunchFailed on graph "
+                         "nodes that take a CUtensorMap parameter); the numbers of such a run are not bench values")
     ap.add_argument("--kernel-rows", type=int, default=12, help="rows of the per-kernel table kept in the JSON line")
     return ap.parse_args()
 
@@ -226,6 +229,9 @@ def run_gcl(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if args.no_graph:                      # profiling aid: same kernels, launched eagerly
+        tr.step_captured = lambda: tr.step(tr.static_x, tr.static_y)
+
     # ---- device-resident throughput
     for _ in range(max(args.warmup, 3)):
         tr.step_captured()
@@ -303,7 +309,8 @@ def run_gcl(args):
                        "parallelism": f"dp{world}", "params": tr.num_params,
                        "l2": f"one activation tensor is {act_mb:.0f} MB per step and ~60 are live (> 126 MB L2): "
                              "inputs larger than L2, no flush needed",
-                       "cuda_graph": "fwd+bwd captured; all-reduce + Adam eager"},
+                       "cuda_graph": ("off (--no-graph, profiling run)" if args.no_graph
+                                      else "fwd+bwd captured; all-reduce + Adam eager")},
             "clocks": clocks,
             "e2e": {"value": world * B / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": world * int(hx.numel() + hy.numel()) * 4, "d2h_bytes_per_step": world * 4,

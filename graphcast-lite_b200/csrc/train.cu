@@ -13,17 +13,18 @@ constexpr int kMaxBlocks = 8 * kNumSMs;
 __global__ void assemble_kernel(const float* __restrict__ x, const float* __restrict__ gs,
                                 const float* __restrict__ ms, float* __restrict__ out, int64_t B, int64_t G,
                                 int64_t M, int TF, int S) {
-  const int W = TF + S;
-  const int64_t total = B * (G + M) * W;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int c = (int)(idx % W);
-    const int64_t rn = idx / W;
+  // a warp per output row (grid-stride), lanes along the channels: one division per row instead of two 64-bit
+  // divisions per element, coalesced row writes
+  const int W = TF + S, lane = threadIdx.x & 31;
+  const int64_t rows = B * (G + M);
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t rn = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; rn < rows; rn += warps) {
     const int64_t n = rn % (G + M), b = rn / (G + M);
-    float v;
-    if (n < G) v = c < TF ? x[(b * G + n) * TF + c] : __ldg(gs + n * S + (c - TF));
-    else v = c < TF ? 0.f : __ldg(ms + (n - G) * S + (c - TF));
-    out[idx] = v;
+    const bool grid_row = n < G;
+    const float* xr = x + (b * G + n) * TF;
+    const float* sr = grid_row ? gs + n * S : ms + (n - G) * S;
+    float* o = out + rn * W;
+    for (int c = lane; c < W; c += 32) o[c] = c < TF ? (grid_row ? xr[c] : 0.f) : __ldg(sr + (c - TF));
   }
 }
 
@@ -89,6 +90,31 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// out[b] = [a[b]; b_[b]] along the node axis (CONCAT) or the reverse (split).  One element = VEC floats of a row
+// segment; segments are contiguous per sample, so each thread walks whole 16-byte words.
+template <typename T, bool CONCAT>
+__global__ void rows_cat_kernel(const T* __restrict__ a_c, const T* __restrict__ b_c, T* __restrict__ x_m,
+                                T* __restrict__ a_m, T* __restrict__ b_m, const T* __restrict__ x_c, int64_t B,
+                                int64_t ea, int64_t eb) {
+  // ea / eb: elements (of T) per sample in the a / b part
+  const int64_t per = ea + eb, total = B * per;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t b = i / per, r = i - b * per;
+    const bool first = r < ea;
+    const int64_t part_idx = first ? b * ea + r : b * eb + (r - ea);
+    if (CONCAT) {
+      const T* src = first ? a_c : b_c;
+      T v{};
+      if (src) v = src[part_idx];
+      x_m[i] = v;
+    } else {
+      T* dst = first ? a_m : b_m;
+      if (dst) dst[part_idx] = x_c[i];
+    }
+  }
+}
+
 int blocks_for(int64_t n) {
   int64_t b = ceil_div(n, kT);
   return (int)(b < 1 ? 1 : (b > kMaxBlocks ? kMaxBlocks : b));
@@ -107,7 +133,7 @@ extern "C" int gcl_assemble_input_f32(const float* x, const float* grid_static, 
                 "gcl_assemble_input_f32: bad sizes");
   const int64_t total = batch * (n_grid + n_mesh) * (tf + s_dim);
   if (total == 0) return GCL_OK;
-  assemble_kernel<<<blocks_for(total), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+  assemble_kernel<<<blocks_for(batch * (n_grid + n_mesh) * 32), kT, 0, static_cast<cudaStream_t>(stream)>>>(
       x, grid_static, mesh_static, enc_in, batch, n_grid, n_mesh, (int)tf, (int)s_dim);
   GCL_CHECK_LAUNCH("gcl_assemble_input_f32");
   return GCL_OK;
@@ -153,4 +179,42 @@ extern "C" int gcl_adam_f32(float* param, const float* grad, float* exp_avg, flo
                                            step_count);
   GCL_CHECK_LAUNCH("gcl_adam_f32");
   return GCL_OK;
+}
+
+namespace {
+template <bool CONCAT>
+int rows_cat(const float* a, const float* b_, float* x, int64_t batch, int64_t na, int64_t nb, int64_t c, void* stream) {
+  const int64_t ea = na * c, eb = nb * c;
+  if (batch == 0 || ea + eb == 0) return GCL_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool v4 = (ea % 4 == 0) && (eb % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b_) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0;
+  if (v4) {
+    const int64_t total = batch * (ea + eb) / 4;
+    gcl::rows_cat_kernel<float4, CONCAT><<<gcl::blocks_for(total), gcl::kT, 0, s>>>(
+        reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b_), reinterpret_cast<float4*>(x),
+        reinterpret_cast<float4*>(const_cast<float*>(a)), reinterpret_cast<float4*>(const_cast<float*>(b_)),
+        reinterpret_cast<const float4*>(x), batch, ea / 4, eb / 4);
+  } else {
+    gcl::rows_cat_kernel<float, CONCAT><<<gcl::blocks_for(batch * (ea + eb)), gcl::kT, 0, s>>>(
+        a, b_, x, const_cast<float*>(a), const_cast<float*>(b_), x, batch, ea, eb);
+  }
+  return GCL_OK;
+}
+}  // namespace
+
+extern "C" int gcl_rows_concat_f32(const float* a, const float* b_, float* out, int64_t batch, int64_t na, int64_t nb,
+                                   int64_t c, void* stream) {
+  GCL_CHECK_ARG(out && batch >= 0 && na >= 0 && nb >= 0 && c > 0, "gcl_rows_concat_f32: bad argument");
+  const int rc = rows_cat<true>(a, b_, out, batch, na, nb, c, stream);
+  GCL_CHECK_LAUNCH("gcl_rows_concat_f32");
+  return rc;
+}
+
+extern "C" int gcl_rows_split_f32(const float* x, float* a, float* b_, int64_t batch, int64_t na, int64_t nb, int64_t c,
+                                  void* stream) {
+  GCL_CHECK_ARG(x && batch >= 0 && na >= 0 && nb >= 0 && c > 0, "gcl_rows_split_f32: bad argument");
+  const int rc = rows_cat<false>(a, b_, const_cast<float*>(x), batch, na, nb, c, stream);
+  GCL_CHECK_LAUNCH("gcl_rows_split_f32");
+  return rc;
 }

@@ -244,7 +244,7 @@ class WeatherPrediction(nn.Module):
         G = self._num_grid_nodes
         enc_in = _AssembleInput.apply(X, self.init_grid_features, self.init_mesh_features)
         enc = self.encoder(X=enc_in, edge_index=self.encoding_graph)
-        grid_lat, mesh_lat = enc[:, :G], enc[:, G:]
+        grid_lat, mesh_lat = ops.split_rows(enc, G)      # contiguous halves, one pass (and one pass back)
         if self.using_sparse_gat:
             proc, new_ei = self.processor(X=mesh_lat, edge_index=self.processing_graph,
                                           attention_threshold=attention_threshold, **kwargs)
@@ -252,6 +252,6 @@ class WeatherPrediction(nn.Module):
         else:
             proc = self.processor(X=mesh_lat, edge_index=self.processing_graph,
                                   attention_threshold=attention_threshold)
-        dec = self.decoder(X=torch.cat((grid_lat, proc), dim=1), edge_index=self.decoding_graph, rows_out=G)
+        dec = self.decoder(X=ops.concat_rows(grid_lat, proc), edge_index=self.decoding_graph, rows_out=G)
         out = dec[:, :G]
         return out.squeeze(0) if squeeze else out

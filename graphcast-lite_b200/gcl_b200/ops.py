@@ -404,6 +404,68 @@ def gat_attend(z, att_src, att_dst, bias, graph, heads, concat, negative_slope, 
     return _GAT.apply(z, att_src, att_dst, bias, graph, heads, concat, negative_slope, want_alpha, prelu_slope)
 
 
+def _rows_concat_raw(a, b, B, na, nb, C, dev):
+    out = torch.empty((B, na + nb, C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("gcl_rows_concat_f32", _p(a), _p(b), _p(out), B, na, nb, C, _stream(), nbytes=8 * B * (na + nb) * C,
+              tag=f"B{B}x({na}+{nb})xC{C}")
+    return out
+
+
+def _rows_split_raw(x, na, want_a=True, want_b=True):
+    B, n, C = x.shape
+    a = torch.empty((B, na, C), dtype=torch.float32, device=x.device) if want_a else None
+    b = torch.empty((B, n - na, C), dtype=torch.float32, device=x.device) if want_b else None
+    with torch.cuda.device(x.device):
+        _call("gcl_rows_split_f32", _p(x), _p(a), _p(b), B, na, n - na, C, _stream(), nbytes=8 * B * n * C,
+              tag=f"B{B}x({na}+{n - na})xC{C}")
+    return a, b
+
+
+class _ConcatRows(torch.autograd.Function):
+    """[B, Na, C], [B, Nb, C] -> [B, Na + Nb, C] (torch.cat(dim=1) of models.py:865) in one pass."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ac, bc = _chk(a, "a"), _chk(b, "b")
+        if ac.dim() != 3 or bc.dim() != 3 or ac.shape[0] != bc.shape[0] or ac.shape[2] != bc.shape[2]:
+            raise ValueError(f"gcl_b200: concat_rows got {tuple(ac.shape)} and {tuple(bc.shape)}")
+        ctx.na = ac.shape[1]
+        return _rows_concat_raw(ac, bc, ac.shape[0], ac.shape[1], bc.shape[1], ac.shape[2], ac.device)
+
+    @staticmethod
+    def backward(ctx, d):
+        return _rows_split_raw(_chk(d, "grad_out"), ctx.na, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+
+
+class _SplitRows(torch.autograd.Function):
+    """[B, N, C] -> contiguous [B, Na, C], [B, N - Na, C] (the slices of models.py:841-842) in one pass."""
+
+    @staticmethod
+    def forward(ctx, x, na):
+        xc = _chk(x, "x")
+        if xc.dim() != 3 or not 0 < int(na) < xc.shape[1]:
+            raise ValueError(f"gcl_b200: split_rows got {tuple(xc.shape)}, na={na}")
+        ctx.shape = xc.shape
+        ctx.na = int(na)
+        return _rows_split_raw(xc, int(na))
+
+    @staticmethod
+    def backward(ctx, da, db):
+        B, n, C = ctx.shape
+        da = _chk(da, "grad_a") if da is not None else None
+        db = _chk(db, "grad_b") if db is not None else None
+        return _rows_concat_raw(da, db, B, ctx.na, n - ctx.na, C, (da if da is not None else db).device), None
+
+
+def concat_rows(a, b):
+    return _ConcatRows.apply(a, b)
+
+
+def split_rows(x, na: int):
+    return _SplitRows.apply(x, na)
+
+
 def edge_prune(ei_pyg: torch.Tensor, alpha_pyg: torch.Tensor, threshold: float) -> torch.Tensor:
     """SparseGATConv pruning (models.py:140-149): edges with alpha >= threshold, order preserved."""
     if not ei_pyg.is_cuda or not alpha_pyg.is_cuda:

@@ -242,6 +242,14 @@ int gcl_closest_face(const double* grid_xyz, const float* mesh_xyz, const int32_
 int gcl_assemble_input_f32(const float* x, const float* grid_static, const float* mesh_static,
                            float* enc_in, int64_t batch, int64_t n_grid, int64_t n_mesh, int64_t tf,
                            int64_t s, void* stream);
+/* Node-axis concat / split of [B, N, C] tensors, one pass each (models.py:841-842 slices the encoder output into
+ * grid / mesh rows, :865 concatenates grid rows and processed mesh rows; each is also the other's backward).
+ *   concat: out[b, :Na] = a[b], out[b, Na:] = b_[b].   split: a[b] = x[b, :Na], b_[b] = x[b, Na:].
+ *   a or b_ may be NULL in split (that part is not needed) and in concat (that part of out is zero-filled). */
+int gcl_rows_concat_f32(const float* a, const float* b_, float* out, int64_t batch, int64_t na, int64_t nb,
+                        int64_t c, void* stream);
+int gcl_rows_split_f32(const float* x, float* a, float* b_, int64_t batch, int64_t na, int64_t nb, int64_t c,
+                       void* stream);
 /* Residual + latitude-weighted MSE (train.py:85-102, 203-213), forward and gradient in one pass:
  *   out = (x_last ? x_last : 0) + delta;  loss = scale * inv_wsum * sum(w (out - y)^2),  w[b,g,c] = lat_w[g]
  *   (lat_w nullable = 1; inv_wsum = 1 / sum of all weights, host-computed);

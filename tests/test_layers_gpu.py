@@ -218,6 +218,27 @@ def test_gat_with_fused_prelu_matches_unfused(B):
         assert_close(p.grad, q.grad, RTOL_F32, f"d{k}", atol=1e-6 if k == "att_dst" else 0.0)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,na,nb,C", [(3, 50, 70, 64), (2, 7, 5, 33), (1, 2048, 10242, 48)])
+def test_rows_concat_split_are_exact_and_inverse(B, na, nb, C):
+    """Node-axis concat / split (models.py:841-842, 865): bit-exact copies, each the other's backward."""
+    from gcl_b200 import ops
+    g = torch.Generator().manual_seed(B * 100 + C)
+    a = torch.randn(B, na, C, generator=g).to(DEV).requires_grad_(True)
+    b = torch.randn(B, nb, C, generator=g).to(DEV).requires_grad_(True)
+    out = ops.concat_rows(a, b)
+    assert torch.equal(out, torch.cat((a, b), dim=1))
+    w = torch.randn(out.shape, generator=g).to(DEV)
+    (out * w).sum().backward()
+    assert torch.equal(a.grad, w[:, :na]) and torch.equal(b.grad, w[:, na:])
+    x = torch.randn(B, na + nb, C, generator=g).to(DEV).requires_grad_(True)
+    p, q = ops.split_rows(x, na)
+    assert p.is_contiguous() and q.is_contiguous()
+    assert torch.equal(p, x[:, :na]) and torch.equal(q, x[:, na:])
+    (q * w[:, na:]).sum().backward()                       # only one half used: the other half's gradient is zero
+    assert torch.equal(x.grad[:, na:], w[:, na:]) and not x.grad[:, :na].any()
+
+
 def test_sparse_gat_subclass_and_prune():
     """The reference's SparseGATConv (models.py:112-151) restated on top of OUR GATConv: subclassing,
     super().forward(..., return_attention_weights=True), threshold mask; plus the fused prune kernel."""
