@@ -92,11 +92,13 @@ class Trainer:
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
         off = 0
+        self._grad_views = []
         for p in params:
             k = p.numel()
             self.flat_param[off:off + k].copy_(p.detach().reshape(-1))
             p.data = self.flat_param[off:off + k].view_as(p)
             p.grad = self.flat_grad[off:off + k].view_as(p)
+            self._grad_views.append(p.grad)
             off += (k + ALIGN - 1) // ALIGN * ALIGN
         self.num_params = sum(p.numel() for p in params)     # trainable scalars (the reference's count)
         self.flat_size = n                                   # incl. alignment padding
@@ -136,6 +138,21 @@ class Trainer:
     def zero_grad(self):
         self.flat_grad.zero_()
 
+    def backward(self, loss: torch.Tensor):
+        """loss.backward() with the gradients landing in the flat buffer through ONE multi-tensor copy: with
+        .grad unset autograd hands each parameter its gradient tensor as is, instead of one `grad += g` kernel per
+        parameter (40-odd tiny launches per step) on top of a zero fill."""
+        for p in self.params:
+            p.grad = None
+        loss.backward()
+        have = [(v, p.grad) for v, p in zip(self._grad_views, self.params) if p.grad is not None]
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for v, p in zip(self._grad_views, self.params):
+            if p.grad is None:
+                v.zero_()                 # parameter not reached by this loss
+            p.grad = v
+
     def reduce_gradients(self):
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
@@ -151,8 +168,8 @@ class Trainer:
 
     # -- CUDA-graph fast path: forward + backward of a fixed batch shape captured once, replayed per step
     def capture(self, batch: int, tf: int, yf: int, attention_threshold: float = 0.0, warmup: int = 2):
-        """Allocate static input buffers [batch, G, tf] / [batch, G, yf] and capture zero_grad + forward +
-        backward into one CUDA graph (every gcl_* entry point is enqueue-only).  The gradient all-reduce
+        """Allocate static input buffers [batch, G, tf] / [batch, G, yf] and capture forward + backward (+ the
+        multi-tensor gradient copy) into one CUDA graph (every gcl_* entry point is enqueue-only).  The gradient all-reduce
         and Adam stay outside the graph (one NCCL call + two tiny kernels)."""
         dev = self.flat_param.device
         self.static_x = torch.zeros(batch, self.G, tf, dtype=torch.float32, device=dev)
@@ -163,17 +180,15 @@ class Trainer:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):      # builds the CSR caches (they sync) before capture
-                self.zero_grad()
-                self.loss(self.static_x, self.static_y, attention_threshold).backward()
+                self.backward(self.loss(self.static_x, self.static_y, attention_threshold))
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         lib = _cabi.load()
         before = lib.gcl_launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.zero_grad()
             self.static_loss = self.loss(self.static_x, self.static_y, attention_threshold)
-            self.static_loss.backward()
+            self.backward(self.static_loss)
         self.launches_in_graph = int(lib.gcl_launch_count() - before)
         return self
 
@@ -192,9 +207,8 @@ class Trainer:
 
     def step(self, X: torch.Tensor, y: torch.Tensor, attention_threshold: float = 0.0, **kwargs) -> torch.Tensor:
         """forward + backward + gradient all-reduce + Adam; returns the (local) loss as a 0-d tensor."""
-        self.zero_grad()
         loss = self.loss(X, y, attention_threshold, **kwargs)
-        loss.backward()
+        self.backward(loss)
         self.reduce_gradients()
         self.optimizer_step()
         return loss.detach()

@@ -311,16 +311,18 @@ def test_cuda_graph_capture_of_forward_backward():
     assert tr.launches_in_graph > 50
     tr.static_x.copy_(X)
     tr.static_y.copy_(y)
-    tr.flat_grad.fill_(123.0)          # the captured zero_grad must wipe this
+    for v in tr._grad_views:
+        v.fill_(123.0)                 # every parameter's gradient must be rewritten by the captured step
     tr.graph.replay()
     torch.cuda.synchronize()
     graph_loss, graph_grad = tr.static_loss.detach().clone(), tr.flat_grad.clone()
     p0 = tr.flat_param.clone()
     tr.zero_grad()
     l0 = tr.loss(X, y)
-    l0.backward()
+    l0.backward()                      # plain autograd accumulation into the zeroed flat buffer
     assert torch.equal(l0.detach(), graph_loss)
     assert torch.equal(tr.flat_grad, graph_grad)
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(tr.params, tr._grad_views))
     # the full captured step also moves the weights (Adam) and leaves the loss readable
     tr.step_captured()
     assert not torch.equal(tr.flat_param, p0) and int(tr.step_count.item()) == 1
