@@ -199,11 +199,40 @@ class Trainer:
         self.optimizer_step()
         return self.static_loss
 
-    def step_from_host(self, X_pinned: torch.Tensor, y_pinned: torch.Tensor) -> float:
-        """End-to-end step from pinned host buffers: H2D copies, captured step, loss read back."""
-        self.static_x.copy_(X_pinned, non_blocking=True)
-        self.static_y.copy_(y_pinned, non_blocking=True)
-        return float(self.step_captured().item())
+    def prefetch(self, X_pinned: torch.Tensor, y_pinned: torch.Tensor):
+        """Start the H2D copy of a batch into staging buffers on a side stream (overlaps whatever the compute
+        stream is doing); the next step_from_host() consumes it with a device-to-device copy."""
+        dev = self.flat_param.device
+        if not hasattr(self, "_stage_x"):
+            self._stage_x, self._stage_y = torch.empty_like(self.static_x), torch.empty_like(self.static_y)
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staged, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(dev))
+        self._copy_stream.wait_event(self._consumed)          # the previous staged batch has left the buffers
+        with torch.cuda.stream(self._copy_stream):
+            self._stage_x.copy_(X_pinned, non_blocking=True)
+            self._stage_y.copy_(y_pinned, non_blocking=True)
+            self._staged.record(self._copy_stream)
+        self._has_staged = True
+
+    def step_from_host(self, X_pinned: torch.Tensor, y_pinned: torch.Tensor, next_batch=None) -> float:
+        """End-to-end step from pinned host buffers: H2D copies, captured step, loss read back.  If the batch was
+        prefetch()ed it is taken from the staging buffers; next_batch = (X, y) starts the following step's H2D
+        copy while this step's kernels run."""
+        cur = torch.cuda.current_stream(self.flat_param.device)
+        if getattr(self, "_has_staged", False):
+            cur.wait_event(self._staged)
+            self.static_x.copy_(self._stage_x, non_blocking=True)
+            self.static_y.copy_(self._stage_y, non_blocking=True)
+            self._consumed.record(cur)
+            self._has_staged = False
+        else:
+            self.static_x.copy_(X_pinned, non_blocking=True)
+            self.static_y.copy_(y_pinned, non_blocking=True)
+        loss = self.step_captured()
+        if next_batch is not None:
+            self.prefetch(*next_batch)
+        return float(loss.item())
 
     def step(self, X: torch.Tensor, y: torch.Tensor, attention_threshold: float = 0.0, **kwargs) -> torch.Tensor:
         """forward + backward + gradient all-reduce + Adam; returns the (local) loss as a 0-d tensor."""

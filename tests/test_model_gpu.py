@@ -326,6 +326,14 @@ def test_cuda_graph_capture_of_forward_backward():
     # the full captured step also moves the weights (Adam) and leaves the loss readable
     tr.step_captured()
     assert not torch.equal(tr.flat_param, p0) and int(tr.step_count.item()) == 1
+    # end-to-end entry: pinned host batch in, loss out; a prefetched batch is consumed from the staging buffers
+    hx, hy = X.cpu().pin_memory(), y.cpu().pin_memory()
+    l1 = tr.step_from_host(hx, hy, next_batch=(hx, hy))
+    assert tr._has_staged
+    tr.static_x.zero_()
+    l2 = tr.step_from_host(hx, hy)
+    assert not tr._has_staged and torch.equal(tr.static_x, X)
+    assert l1 > 0 and l2 > 0 and l2 < l1 and int(tr.step_count.item()) == 3
 
 
 def test_import_swap_reference_glue_on_gcl_layers():
