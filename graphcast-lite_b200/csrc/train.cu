@@ -12,10 +12,11 @@ constexpr int kMaxBlocks = 8 * kNumSMs;
 
 __global__ void assemble_kernel(const float* __restrict__ x, const float* __restrict__ gs,
                                 const float* __restrict__ ms, float* __restrict__ out, int64_t B, int64_t G,
-                                int64_t M, int TF, int S) {
+                                int64_t M, int TF, int S, int W) {
   // a warp per output row (grid-stride), lanes along the channels: one division per row instead of two 64-bit
   // divisions per element, coalesced row writes
-  const int W = TF + S, lane = threadIdx.x & 31;
+  // W >= TF + S is the output row width; columns past TF + S are zero (alignment padding)
+  const int lane = threadIdx.x & 31;
   const int64_t rows = B * (G + M);
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t rn = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; rn < rows; rn += warps) {
@@ -24,7 +25,8 @@ __global__ void assemble_kernel(const float* __restrict__ x, const float* __rest
     const float* xr = x + (b * G + n) * TF;
     const float* sr = grid_row ? gs + n * S : ms + (n - G) * S;
     float* o = out + rn * W;
-    for (int c = lane; c < W; c += 32) o[c] = c < TF ? (grid_row ? xr[c] : 0.f) : __ldg(sr + (c - TF));
+    for (int c = lane; c < W; c += 32)
+      o[c] = c < TF ? (grid_row ? xr[c] : 0.f) : (c < TF + S ? __ldg(sr + (c - TF)) : 0.f);
   }
 }
 
@@ -127,14 +129,16 @@ using namespace gcl;
 
 extern "C" int gcl_assemble_input_f32(const float* x, const float* grid_static, const float* mesh_static,
                                       float* enc_in, int64_t batch, int64_t n_grid, int64_t n_mesh, int64_t tf,
-                                      int64_t s_dim, void* stream) {
+                                      int64_t s_dim, int64_t out_width, void* stream) {
   GCL_CHECK_ARG(x && grid_static && mesh_static && enc_in, "gcl_assemble_input_f32: null pointer argument");
   GCL_CHECK_ARG(batch >= 0 && n_grid >= 0 && n_mesh >= 0 && tf >= 0 && s_dim >= 0 && tf + s_dim > 0,
                 "gcl_assemble_input_f32: bad sizes");
-  const int64_t total = batch * (n_grid + n_mesh) * (tf + s_dim);
+  GCL_CHECK_ARG(out_width >= tf + s_dim, "gcl_assemble_input_f32: out_width %lld < tf + s = %lld", (long long)out_width,
+                (long long)(tf + s_dim));
+  const int64_t total = batch * (n_grid + n_mesh) * out_width;
   if (total == 0) return GCL_OK;
   assemble_kernel<<<blocks_for(batch * (n_grid + n_mesh) * 32), kT, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, grid_static, mesh_static, enc_in, batch, n_grid, n_mesh, (int)tf, (int)s_dim);
+      x, grid_static, mesh_static, enc_in, batch, n_grid, n_mesh, (int)tf, (int)s_dim, (int)out_width);
   GCL_CHECK_LAUNCH("gcl_assemble_input_f32");
   return GCL_OK;
 }

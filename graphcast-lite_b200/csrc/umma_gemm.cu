@@ -708,7 +708,14 @@ __global__ void __launch_bounds__(kLtThreads, 1)
     umma_linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
                            const __grid_constant__ CUtensorMap tmZ, const float* __restrict__ W, int64_t M, int N,
                            int K, int n_pad, int nkb, int nob, int s_raw, int s_lo, int nbuf, int tmem_cols, int has_z,
-                           const float* __restrict__ bias, const float* __restrict__ prelu_slope) {
+                           const float* __restrict__ bias, const float* __restrict__ prelu_slope, int n_split) {
+  // n_split = 2: W (hi + lo) of a wide layer does not fit next to the operand ring, so CTA 2c and 2c + 1 walk the
+  // same row tiles and each owns one half of the output columns (N is then the half width).  The second read of
+  // a tile comes out of L2: HBM traffic stays what it was.
+  const int half = blockIdx.x % n_split, cta = blockIdx.x / n_split, ncta = gridDim.x / n_split;
+  W += (int64_t)half * N * K;
+  if (bias) bias += half * N;
+  const int col0 = half * N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_block = n_pad * 128;
@@ -728,7 +735,7 @@ __global__ void __launch_bounds__(kLtThreads, 1)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (M + kTileM - 1) / kTileM;
-  const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_tiles = (ntiles > cta) ? (ntiles - cta + ncta - 1) / ncta : 0;
   const int64_t my_items = my_tiles * nkb;
 
   if (tid == 0) {
@@ -766,7 +773,7 @@ __global__ void __launch_bounds__(kLtThreads, 1)
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 1;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int64_t tile = cta; tile < ntiles; tile += ncta) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(bar(kRawEmpty + s), ph);
           mbar_expect_tx(bar(kRawFull + s), kSlabBytes);
@@ -804,7 +811,7 @@ __global__ void __launch_bounds__(kLtThreads, 1)
     int rs = 0, ls = 0;
     uint32_t rph = 0, lph = 0;
     int64_t t_local = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_local) {
+    for (int64_t tile = cta; tile < ntiles; tile += ncta, ++t_local) {
       const int acc = (int)(t_local & 1);
       mbar_wait(bar(kAccEmpty + acc), (uint32_t)(((t_local >> 1) & 1) ^ 1));
       tc_fence_after();
@@ -838,7 +845,7 @@ __global__ void __launch_bounds__(kLtThreads, 1)
     const float slope = prelu_slope ? __ldg(prelu_slope) : 0.f;
     const int my = (warp & 3) * 32 + lane, cgrp = warp >> 2;
     int64_t t_local = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_local) {
+    for (int64_t tile = cta; tile < ntiles; tile += ncta, ++t_local) {
       const int acc = (int)(t_local & 1);
       uint8_t* ob = c_out + (size_t)(nbuf == 2 ? (t_local & 1) : 0) * out_buf_bytes;
       uint8_t* zb = ob + (size_t)nob * kSlabBytes;
@@ -872,8 +879,8 @@ __global__ void __launch_bounds__(kLtThreads, 1)
       named_bar(1, kLtEpiThreads);
       if (tid == 0) {
         for (int j = 0; j < nob; ++j) {
-          tma_store_2d(&tmC, j * kKB, (int)(tile * kTileM), smem_u32(ob + (size_t)j * kSlabBytes));
-          if (has_z) tma_store_2d(&tmZ, j * kKB, (int)(tile * kTileM), smem_u32(zb + (size_t)j * kSlabBytes));
+          tma_store_2d(&tmC, col0 + j * kKB, (int)(tile * kTileM), smem_u32(ob + (size_t)j * kSlabBytes));
+          if (has_z) tma_store_2d(&tmZ, col0 + j * kKB, (int)(tile * kTileM), smem_u32(zb + (size_t)j * kSlabBytes));
         }
         bulk_commit();
       }
@@ -1202,7 +1209,12 @@ int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int6
                     const float* slope, float* z_out, cudaStream_t s) {
   if (!(al16(A) && al16(W_nk) && al16(C) && (!z_out || al16(z_out))) || M <= 0 || M > 0x7fffff00LL)
     return GCL_ERR_UNSUPPORTED;
-  const TmaLinPlan p = plan_linear_tma(N, K, z_out != nullptr);
+  TmaLinPlan p = plan_linear_tma(N, K, z_out != nullptr);
+  int n_split = 1;
+  if (!p.ok && N % 64 == 0) {            // too wide for one CTA's smem: two CTAs per row tile, half the columns each
+    p = plan_linear_tma(N / 2, K, z_out != nullptr);
+    n_split = 2;
+  }
   if (!p.ok) return GCL_ERR_UNSUPPORTED;
   CUtensorMap tmA, tmC, tmZ;
   if (!make_map_2d(&tmA, A, M, K, kTileM, kKB, CU_TENSOR_MAP_SWIZZLE_128B) ||
@@ -1210,13 +1222,14 @@ int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int6
       !make_map_2d(&tmZ, z_out ? z_out : C, M, N, kTileM, kKB, CU_TENSOR_MAP_SWIZZLE_128B))
     return GCL_ERR_UNSUPPORTED;
   const int64_t ntiles = (M + kTileM - 1) / kTileM;
-  const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+  const int64_t per = kNumSMs / n_split;
+  const int grid = (int)(ntiles < per ? ntiles : per) * n_split;
   cudaError_t e =
       cudaFuncSetAttribute(umma_linear_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return fail_cuda(e, "umma_linear_tma(smem attr)");
-  umma_linear_tma_kernel<<<grid, kLtThreads, p.smem, s>>>(tmA, tmC, tmZ, W_nk, M, (int)N, (int)K, p.n_pad, p.nkb,
-                                                          p.nob, p.s_raw, p.s_lo, p.nbuf, p.tmem_cols, z_out ? 1 : 0,
-                                                          bias, slope);
+  umma_linear_tma_kernel<<<grid, kLtThreads, p.smem, s>>>(tmA, tmC, tmZ, W_nk, M, (int)(N / n_split), (int)K, p.n_pad,
+                                                          p.nkb, p.nob, p.s_raw, p.s_lo, p.nbuf, p.tmem_cols,
+                                                          z_out ? 1 : 0, bias, slope, n_split);
   GCL_CHECK_LAUNCH("umma_linear_tma");
   return GCL_OK;
 }

@@ -48,7 +48,7 @@ _PROTOS = {
     "gcl_radius_query_count": (c_int, [P, P, I64, I64, ctypes.c_double, P, P, SZ, P]),
     "gcl_radius_query_fill": (c_int, [P, P, I64, I64, ctypes.c_double, P, P, I64, I64, P]),
     "gcl_closest_face": (c_int, [P, P, P, I64, I64, I64, ctypes.c_double, P, P]),
-    "gcl_assemble_input_f32": (c_int, [P, P, P, P, I64, I64, I64, I64, I64, P]),
+    "gcl_assemble_input_f32": (c_int, [P, P, P, P, I64, I64, I64, I64, I64, I64, P]),
     "gcl_rows_concat_f32": (c_int, [P, P, P, I64, I64, I64, I64, P]),
     "gcl_rows_split_f32": (c_int, [P, P, P, I64, I64, I64, I64, P]),
     "gcl_wmse_workspace_bytes": (SZ, [I64, I64, I64]),

@@ -49,10 +49,10 @@ class MLP(nn.Module):
             if isinstance(m, nn.Linear):
                 nxt = mods[i + 1] if i + 1 < len(mods) else None
                 if isinstance(nxt, nn.PReLU):
-                    X = ops.linear(X, m.weight, m.bias, nxt.weight)   # fused Linear + bias + PReLU
+                    X = ops.linear(X, _fit(m.weight, X), m.bias, nxt.weight)   # fused Linear + bias + PReLU
                     i += 2
                     continue
-                X = ops.linear(X, m.weight, m.bias)
+                X = ops.linear(X, _fit(m.weight, X), m.bias)
             elif isinstance(m, nn.PReLU):
                 X = ops.prelu(X, m.weight)
             else:
@@ -132,7 +132,7 @@ class GraphLayer(nn.Module):
             fuse = isinstance(nxt, nn.PReLU)
             if type(m) is GCNConv:
                 g = GLOBAL_CACHE.get(edge_index, n, CSR_LOOPS)
-                W, b, C = m.lin.weight, m.bias, m.out_channels
+                W, b, C = _fit(m.lin.weight, X), m.bias, m.out_channels
                 if C % 4:
                     # rows of 4k+r floats would force every kernel of this layer onto its scalar path: compute a
                     # zero-padded 4-aligned layer (extra output channels are exactly 0) and slice the result
@@ -178,22 +178,29 @@ class Model(nn.Module):
         return self.graph_layer(X=X, edge_index=edge_index, attention_threshold=attention_threshold, **kwargs)
 
 
+def _fit(W, X):
+    """Weight [out, in] widened with zero columns to the (zero-padded) input width."""
+    extra = X.shape[-1] - W.shape[1]
+    return F.pad(W, (0, extra)) if extra > 0 else W
+
+
 class _AssembleInput(torch.autograd.Function):
     """[B,G,TF] -> [B,G+M,TF+S]: grid rows get their static features appended, mesh rows are
     zeros + static features (models.py:776-806), written by one kernel."""
 
     @staticmethod
-    def forward(ctx, x, grid_static, mesh_static):
+    def forward(ctx, x, grid_static, mesh_static, width=None):
         if not x.is_cuda or x.dtype != torch.float32:
             raise RuntimeError("gcl_b200: model input must be a float32 CUDA tensor; no CPU fallback")
         x = x.contiguous()
         B, G, TF = x.shape
         M, S = mesh_static.shape
-        out = torch.empty((B, G + M, TF + S), dtype=torch.float32, device=x.device)
+        width = TF + S if width is None else int(width)
+        out = torch.empty((B, G + M, width), dtype=torch.float32, device=x.device)
         lib = _cabi.load()
         with torch.cuda.device(x.device):
             _cabi.check(lib.gcl_assemble_input_f32(x.data_ptr(), grid_static.data_ptr(), mesh_static.data_ptr(),
-                                                   out.data_ptr(), B, G, M, TF, S,
+                                                   out.data_ptr(), B, G, M, TF, S, width,
                                                    torch.cuda.current_stream().cuda_stream),
                         "gcl_assemble_input_f32")
         ctx.G, ctx.TF = G, TF
@@ -201,7 +208,7 @@ class _AssembleInput(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d):
-        return d[:, : ctx.G, : ctx.TF].contiguous(), None, None
+        return d[:, : ctx.G, : ctx.TF].contiguous(), None, None, None
 
 
 class WeatherPrediction(nn.Module):
@@ -229,6 +236,8 @@ class WeatherPrediction(nn.Module):
         self.encoder = Model(pipe["encoder"], self.total_feature_size + self.init_grid_features.shape[1])
         self.processor = Model(pipe["processor"], self.encoder.output_dim)
         self.decoder = Model(pipe["decoder"], self.processor.output_dim)
+        first = self.encoder.mlp.MLP[0] if self.encoder.mlp is not None else self.encoder.graph_layer.layers[0]
+        self._pad_input = type(first) in (nn.Linear, GCNConv)       # both take a zero-padded weight (_fit)
         self.to(self.device)
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -242,7 +251,11 @@ class WeatherPrediction(nn.Module):
         elif X.dim() == 3 and X.size(0) == 1:
             squeeze = True                       # the reference returns [G, F] for its batch of one
         G = self._num_grid_nodes
-        enc_in = _AssembleInput.apply(X, self.init_grid_features, self.init_mesh_features)
+        # rows padded to a multiple of 4 floats (zeros) when the first consumer can take a zero-padded weight
+        width = self.total_feature_size + self.init_grid_features.shape[1]
+        if self._pad_input:
+            width = (width + 3) // 4 * 4
+        enc_in = _AssembleInput.apply(X, self.init_grid_features, self.init_mesh_features, width)
         enc = self.encoder(X=enc_in, edge_index=self.encoding_graph)
         grid_lat, mesh_lat = ops.split_rows(enc, G)      # contiguous halves, one pass (and one pass back)
         if self.using_sparse_gat:

@@ -238,10 +238,11 @@ int gcl_closest_face(const double* grid_xyz, const float* mesh_xyz, const int32_
 /* ------------------------------------------------------------------------------------------------
  * a9/a14  glue of one forecast / training step (models.py:776-806, train.py:85-102,203-213; Adam).
  */
-/* enc_in[b, n, :] = n < G ? [x[b,n,:TF], grid_static[n,:S]] : [0..0, mesh_static[n-G,:S]] */
+/* enc_in[b, n, :] = n < G ? [x[b,n,:TF], grid_static[n,:S], 0..] : [0..0, mesh_static[n-G,:S], 0..];
+ * rows are out_width >= TF + S floats wide, the tail is zero (lets the caller keep rows 16-byte aligned). */
 int gcl_assemble_input_f32(const float* x, const float* grid_static, const float* mesh_static,
                            float* enc_in, int64_t batch, int64_t n_grid, int64_t n_mesh, int64_t tf,
-                           int64_t s, void* stream);
+                           int64_t s, int64_t out_width, void* stream);
 /* Node-axis concat / split of [B, N, C] tensors, one pass each (models.py:841-842 slices the encoder output into
  * grid / mesh rows, :865 concatenates grid rows and processed mesh rows; each is also the other's backward).
  *   concat: out[b, :Na] = a[b], out[b, Na:] = b_[b].   split: a[b] = x[b, :Na], b_[b] = x[b, Na:].
