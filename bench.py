@@ -284,8 +284,14 @@ def run_gcl(args):
                               "algo_GBps": gbs, "frac_hbm": gbs / peak})
         (name, tag), a = rows[0]
         gbs = a["bytes"] / (a["ms"] * 1e-3) / 1e9
+        traffic = None
+        try:    # measured DRAM bytes per launch of this kernel, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+                traffic = json.load(f).get(f"{name}[{tag}]")
+        except (OSError, ValueError):
+            pass
         roof = {"kernel": f"{name}[{tag}]", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                "frac": gbs / peak, "traffic": None, "peak_source": peak_src,
+                "frac": gbs / peak, "traffic": traffic, "peak_source": peak_src,
                 "share_of_step_kernel_time": a["ms"] / total,
                 "algorithmic_bytes_per_launch": a["bytes"] / a["calls"], "us_per_launch": 1e3 * a["ms"] / a["calls"]}
         # mesh message passing edges/s of the processor's aggregation kernel (forward)
