@@ -708,7 +708,13 @@ __global__ void __launch_bounds__(kLtThreads, 1)
     umma_linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
                            const __grid_constant__ CUtensorMap tmZ, const float* __restrict__ W, int64_t M, int N,
                            int K, int n_pad, int nkb, int nob, int s_raw, int s_lo, int nbuf, int tmem_cols, int has_z,
-                           const float* __restrict__ bias, const float* __restrict__ prelu_slope, int n_split) {
+                           const float* __restrict__ bias, const float* __restrict__ prelu_slope, int n_split,
+                           const __grid_constant__ CUtensorMap tmZin, const float* __restrict__ act_slope,
+                           float* __restrict__ dslope_part) {
+  // act_slope != nullptr (used for dX): the result is multiplied by PReLU'(z_in) of the layer that produced this
+  // layer's input, z_in tiles arrive by TMA like A, and sum(result * min(z_in, 0)) -- that PReLU's slope
+  // gradient -- leaves as one partial per CTA.  Saves the separate pass over dX, z_in and dZ.
+  const int has_act = act_slope != nullptr;
   // n_split = 2: W (hi + lo) of a wide layer does not fit next to the operand ring, so CTA 2c and 2c + 1 walk the
   // same row tiles and each owns one half of the output columns (N is then the half width).  The second read of
   // a tile comes out of L2: HBM traffic stays what it was.
@@ -725,12 +731,14 @@ __global__ void __launch_bounds__(kLtThreads, 1)
   uint8_t* lo = raw + (size_t)s_raw * kSlabBytes;
   uint8_t* c_out = lo + (size_t)s_lo * kSlabBytes;                     // [nbuf][1 + has_z][nob] slabs
   const int out_buf_bytes = (1 + has_z) * nob * kSlabBytes;
-  float* bias_s = reinterpret_cast<float*>(c_out + (size_t)nbuf * out_buf_bytes);
+  uint8_t* zin = c_out + (size_t)nbuf * out_buf_bytes;                 // [nob] slabs of z_in, single-buffered
+  float* bias_s = reinterpret_cast<float*>(zin + (size_t)(has_act ? nob : 0) * kSlabBytes);
   uint64_t* bar_ptr = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bias_s + n_pad) + 15) & ~uintptr_t(15));
   const uint32_t bars = smem_u32(bar_ptr);
   const int kRawFull = 0, kRawEmpty = s_raw, kLoFull = 2 * s_raw, kLoEmpty = 2 * s_raw + s_lo,
             kAccFull = 2 * s_raw + 2 * s_lo, kAccEmpty = kAccFull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + kAccEmpty + 2);
+  const int kZinFull = kAccEmpty + 2, kZinEmpty = kZinFull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + kZinEmpty + 1);
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -751,6 +759,8 @@ __global__ void __launch_bounds__(kLtThreads, 1)
       mbar_init(bar(kAccFull + a), 1);
       mbar_init(bar(kAccEmpty + a), kLtEpiThreads);
     }
+    mbar_init(bar(kZinFull), 1);
+    mbar_init(bar(kZinEmpty), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kLtMmaWarp) tmem_alloc(smem_u32(tmem_slot), (uint32_t)tmem_cols);
@@ -843,7 +853,17 @@ __global__ void __launch_bounds__(kLtThreads, 1)
     // it) until the PREVIOUS tile's stores have finished reading their buffer, which is the one the NEXT tile
     // writes.  With one buffer (not enough smem for two) that wait has to sit in front of the writes.
     const float slope = prelu_slope ? __ldg(prelu_slope) : 0.f;
+    const float aslope = has_act ? __ldg(act_slope) : 0.f;
+    float dsl = 0.f;
     const int my = (warp & 3) * 32 + lane, cgrp = warp >> 2;
+    // z_in tiles are fetched by epilogue thread 0 itself, one tile ahead (right after the barrier that says every
+    // thread is done with the previous one), so the A producer never waits on the epilogue
+    auto fetch_zin = [&](int64_t tile) {
+      mbar_expect_tx(bar(kZinFull), (uint32_t)nob * kSlabBytes);
+      for (int j = 0; j < nob; ++j)
+        tma_load_2d(smem_u32(zin + (size_t)j * kSlabBytes), &tmZin, col0 + j * kKB, (int)(tile * kTileM), bar(kZinFull));
+    };
+    if (has_act && tid == 0 && cta < ntiles) fetch_zin(cta);
     int64_t t_local = 0;
     for (int64_t tile = cta; tile < ntiles; tile += ncta, ++t_local) {
       const int acc = (int)(t_local & 1);
@@ -855,6 +875,8 @@ __global__ void __launch_bounds__(kLtThreads, 1)
       }
       mbar_wait(bar(kAccFull + acc), (uint32_t)((t_local >> 1) & 1));
       tc_fence_after();
+      if (has_act) mbar_wait(bar(kZinFull), (uint32_t)(t_local & 1));
+      const bool row_ok = tile * kTileM + my < M;          // rows past M hold zero-filled z_in: keep them out of dsl
       const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * 2 * n_pad);
       for (int c0 = cgrp * 16; c0 < n_pad; c0 += 32) {
         float v[16], vc[16];
@@ -866,6 +888,14 @@ __global__ void __launch_bounds__(kLtThreads, 1)
           const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col);
           float4 o = make_float4((v[4 * q] + vc[4 * q]) + b4.x, (v[4 * q + 1] + vc[4 * q + 1]) + b4.y,
                                  (v[4 * q + 2] + vc[4 * q + 2]) + b4.z, (v[4 * q + 3] + vc[4 * q + 3]) + b4.w);
+          if (has_act) {
+            const float4 zv = *reinterpret_cast<const float4*>(zin + off);
+            if (row_ok && col < N)
+              dsl += (zv.x > 0.f ? 0.f : o.x * zv.x) + (zv.y > 0.f ? 0.f : o.y * zv.y) + (zv.z > 0.f ? 0.f : o.z * zv.z) +
+                     (zv.w > 0.f ? 0.f : o.w * zv.w);
+            o = make_float4(zv.x > 0.f ? o.x : aslope * o.x, zv.y > 0.f ? o.y : aslope * o.y, zv.z > 0.f ? o.z : aslope * o.z,
+                            zv.w > 0.f ? o.w : aslope * o.w);
+          }
           if (has_z) *reinterpret_cast<float4*>(zb + off) = o;
           if (prelu_slope)
             o = make_float4(prelu_f(o.x, slope), prelu_f(o.y, slope), prelu_f(o.z, slope), prelu_f(o.w, slope));
@@ -878,11 +908,24 @@ __global__ void __launch_bounds__(kLtThreads, 1)
       if (nbuf == 2 && tid == 0) bulk_wait_read();
       named_bar(1, kLtEpiThreads);
       if (tid == 0) {
+        if (has_act && tile + ncta < ntiles) fetch_zin(tile + ncta);   // everyone has read this tile's z_in
         for (int j = 0; j < nob; ++j) {
           tma_store_2d(&tmC, col0 + j * kKB, (int)(tile * kTileM), smem_u32(ob + (size_t)j * kSlabBytes));
           if (has_z) tma_store_2d(&tmZ, col0 + j * kKB, (int)(tile * kTileM), smem_u32(zb + (size_t)j * kSlabBytes));
         }
         bulk_commit();
+      }
+    }
+    if (has_act) {                                         // per-CTA slope-gradient partial, fixed order
+      __shared__ float dsl_s[kLtEpiWarps];
+      dsl = warp_sum(dsl);
+      if (lane == 0) dsl_s[warp] = dsl;
+      named_bar(1, kLtEpiThreads);
+      if (tid == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLtEpiWarps; ++w) t += dsl_s[w];
+        dslope_part[blockIdx.x] = t;
       }
     }
     if (tid == 0) bulk_wait_all();
@@ -1177,7 +1220,7 @@ struct TmaLinPlan {
   size_t smem;
   bool ok;
 };
-TmaLinPlan plan_linear_tma(int64_t N, int64_t K, bool has_z) {
+TmaLinPlan plan_linear_tma(int64_t N, int64_t K, bool has_z, bool has_act = false) {
   TmaLinPlan p{};
   p.n_pad = (int)((N + 15) / 16 * 16);
   p.nkb = (int)((K + kKB - 1) / kKB);
@@ -1187,7 +1230,7 @@ TmaLinPlan plan_linear_tma(int64_t N, int64_t K, bool has_z) {
   const long fixed = 1024 + 512 + 4L * p.n_pad;
   long slabs = 0, out_bytes = 0;
   for (p.nbuf = 2; p.nbuf >= 1; --p.nbuf) {       // two output buffers if at least 7 operand slabs remain
-    out_bytes = (long)p.nbuf * p.nob * kSlabBytes * (has_z ? 2 : 1);
+    out_bytes = (long)p.nbuf * p.nob * kSlabBytes * (has_z ? 2 : 1) + (has_act ? (long)p.nob * kSlabBytes : 0);
     slabs = ((long)kMaxSmem - w_bytes - out_bytes - fixed) / kSlabBytes;
     if (slabs >= (p.nbuf == 2 ? 7 : 5)) break;
   }
@@ -1206,20 +1249,23 @@ TmaLinPlan plan_linear_tma(int64_t N, int64_t K, bool has_z) {
 }
 
 int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
-                    const float* slope, float* z_out, cudaStream_t s) {
+                    const float* slope, float* z_out, const float* z_in, const float* act_slope, float* dslope_part,
+                    int* n_parts, cudaStream_t s) {
+  if (act_slope && (!z_in || !dslope_part || !al16(z_in) || z_out)) return GCL_ERR_UNSUPPORTED;
   if (!(al16(A) && al16(W_nk) && al16(C) && (!z_out || al16(z_out))) || M <= 0 || M > 0x7fffff00LL)
     return GCL_ERR_UNSUPPORTED;
-  TmaLinPlan p = plan_linear_tma(N, K, z_out != nullptr);
+  TmaLinPlan p = plan_linear_tma(N, K, z_out != nullptr, act_slope != nullptr);
   int n_split = 1;
   if (!p.ok && N % 64 == 0) {            // too wide for one CTA's smem: two CTAs per row tile, half the columns each
-    p = plan_linear_tma(N / 2, K, z_out != nullptr);
+    p = plan_linear_tma(N / 2, K, z_out != nullptr, act_slope != nullptr);
     n_split = 2;
   }
   if (!p.ok) return GCL_ERR_UNSUPPORTED;
-  CUtensorMap tmA, tmC, tmZ;
+  CUtensorMap tmA, tmC, tmZ, tmZin;
   if (!make_map_2d(&tmA, A, M, K, kTileM, kKB, CU_TENSOR_MAP_SWIZZLE_128B) ||
       !make_map_2d(&tmC, C, M, N, kTileM, kKB, CU_TENSOR_MAP_SWIZZLE_128B) ||
-      !make_map_2d(&tmZ, z_out ? z_out : C, M, N, kTileM, kKB, CU_TENSOR_MAP_SWIZZLE_128B))
+      !make_map_2d(&tmZ, z_out ? z_out : C, M, N, kTileM, kKB, CU_TENSOR_MAP_SWIZZLE_128B) ||
+      !make_map_2d(&tmZin, z_in ? z_in : C, M, N, kTileM, kKB, CU_TENSOR_MAP_SWIZZLE_128B))
     return GCL_ERR_UNSUPPORTED;
   const int64_t ntiles = (M + kTileM - 1) / kTileM;
   const int64_t per = kNumSMs / n_split;
@@ -1229,7 +1275,9 @@ int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int6
   if (e != cudaSuccess) return fail_cuda(e, "umma_linear_tma(smem attr)");
   umma_linear_tma_kernel<<<grid, kLtThreads, p.smem, s>>>(tmA, tmC, tmZ, W_nk, M, (int)(N / n_split), (int)K, p.n_pad,
                                                           p.nkb, p.nob, p.s_raw, p.s_lo, p.nbuf, p.tmem_cols,
-                                                          z_out ? 1 : 0, bias, slope, n_split);
+                                                          z_out ? 1 : 0, bias, slope, n_split, tmZin, act_slope,
+                                                          dslope_part);
+  if (n_parts) *n_parts = grid;
   GCL_CHECK_LAUNCH("umma_linear_tma");
   return GCL_OK;
 }
@@ -1238,9 +1286,14 @@ int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int6
 // Returns GCL_OK when launched, GCL_ERR_UNSUPPORTED when the shape does not fit (caller falls back to
 // the FFMA kernel), or an error.
 int umma_linear(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
-                const float* slope, float* z_out, cudaStream_t s) {
+                const float* slope, float* z_out, cudaStream_t s, const float* z_in, const float* act_slope,
+                float* dslope_part, int* n_parts) {
+  if (act_slope) {   // only the TMA kernel has the fused PReLU-backward epilogue
+    if (g_force_register_staging) return GCL_ERR_UNSUPPORTED;
+    return umma_linear_tma(A, W_nk, C, M, N, K, bias, slope, z_out, z_in, act_slope, dslope_part, n_parts, s);
+  }
   if (!g_force_register_staging) {
-    const int rc = umma_linear_tma(A, W_nk, C, M, N, K, bias, slope, z_out, s);
+    const int rc = umma_linear_tma(A, W_nk, C, M, N, K, bias, slope, z_out, nullptr, nullptr, nullptr, nullptr, s);
     if (rc != GCL_ERR_UNSUPPORTED) return rc;
   }
   LinPlan p = plan_linear(N, K, z_out != nullptr, al16(C) && (!z_out || al16(z_out)));

@@ -23,6 +23,8 @@ _PROTOS = {
     "gcl_spmm_f32": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "gcl_linear_fwd_f32": (c_int, [P, P, P, P, I64, I64, I64, P, P, P, P]),
     "gcl_linear_bwd_dx_f32": (c_int, [P, P, P, I64, I64, I64, P, P]),
+    "gcl_linear_bwd_dx_prelu_workspace_bytes": (c_size_t, [I64, I64]),
+    "gcl_linear_bwd_dx_prelu_f32": (c_int, [P, P, P, P, P, P, I64, I64, I64, P, P, c_size_t, P]),
     "gcl_set_dense_mode": (c_int, [I32]),
     "gcl_get_dense_mode": (c_int, []),
     "gcl_linear_bwd_dw_workspace_bytes": (SZ, [I64, I64, I64]),

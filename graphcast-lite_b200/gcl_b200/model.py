@@ -42,22 +42,33 @@ class MLP(nn.Module):
             self.MLP.append(LayerNorm(cfg["output_dim"], mode=cfg.get("layer_norm_mode") or "graph"))
 
     def forward(self, X):
+        # Linear + bias + PReLU is one kernel that writes the pre-activation z and a = PReLU(z); the chain is
+        # differentiated through z, and each PReLU's backward runs inside the NEXT Linear's dX kernel
+        # (ops._ActLinear).  (z, slope) is the pending activation whose output X currently is.
         mods = list(self.MLP)
-        i = 0
+        i, z, slope = 0, None, None
         while i < len(mods):
             m = mods[i]
             if isinstance(m, nn.Linear):
                 nxt = mods[i + 1] if i + 1 < len(mods) else None
-                if isinstance(nxt, nn.PReLU):
-                    X = ops.linear(X, _fit(m.weight, X), m.bias, nxt.weight)   # fused Linear + bias + PReLU
+                so = nxt.weight if isinstance(nxt, nn.PReLU) else None
+                res = ops.act_linear(z, X, slope, _fit(m.weight, X), m.bias, so)
+                if so is not None:
+                    (z, X), slope = res, so
                     i += 2
-                    continue
-                X = ops.linear(X, _fit(m.weight, X), m.bias)
-            elif isinstance(m, nn.PReLU):
+                else:
+                    X, z, slope = res, None, None
+                    i += 1
+                continue
+            if z is not None:                  # someone other than a Linear consumes the activation: make it a
+                X, z, slope = ops.prelu(z, slope), None, None      # differentiable tensor again
+            if isinstance(m, nn.PReLU):
                 X = ops.prelu(X, m.weight)
             else:
                 X = m(X)
             i += 1
+        if z is not None:
+            X = ops.prelu(z, slope)
         return X
 
 

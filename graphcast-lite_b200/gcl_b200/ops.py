@@ -153,6 +153,23 @@ def linear_bwd_dx_raw(dy2, W):
     return dx
 
 
+def linear_bwd_dx_prelu_raw(dy2, W, z_in2, slope):
+    """dz_in = (dy W) * PReLU'(z_in), dslope: backward of PReLU -> Linear w.r.t. the PReLU input, one kernel."""
+    R, cout = dy2.shape
+    cin = W.shape[1]
+    dz = torch.empty((R, cin), dtype=torch.float32, device=dy2.device)
+    dslope = torch.empty(1, dtype=torch.float32, device=dy2.device)
+    scratch = torch.empty(cin * cout, dtype=torch.float32, device=dy2.device)
+    lib = _cabi.load()
+    nb = lib.gcl_linear_bwd_dx_prelu_workspace_bytes(R, cin)
+    ws = _ws(nb, dy2.device)
+    with torch.cuda.device(dy2.device):
+        _call("gcl_linear_bwd_dx_prelu_f32", _p(dy2), _p(W), _p(z_in2), _p(slope), _p(dz), _p(dslope), R, cin, cout,
+              _p(scratch), _p(ws), nb, _stream(), nbytes=4 * R * (2 * cin + cout) + 4 * cin * cout,
+              tag=f"R{R}x{cout}->{cin}")
+    return dz, dslope
+
+
 def linear_bwd_dw_raw(dy2, x2, want_bias):
     R, cout = dy2.shape
     cin = x2.shape[1]
@@ -250,6 +267,54 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dW, db = linear_bwd_dw_raw(d2, x2, ctx.has_bias)
         return dx, dW, (db if ctx.has_bias else None), (dslope if ctx.has_slope else None)
+
+
+class _ActLinear(torch.autograd.Function):
+    """y = Linear(a_in) where a_in = PReLU(z_in) was produced (together with z_in) by the previous layer's fused
+    epilogue.  Autograd sees the chain through the PRE-activations: the input that carries gradient is z_in, and
+    the PReLU's backward runs in the epilogue of this layer's dX GEMM.  With slope_out the layer returns
+    (z_out [differentiable], a_out = PReLU(z_out) [buffer for the next _ActLinear]); without, just y.
+    z_in = None: a_in is an ordinary differentiable input."""
+
+    @staticmethod
+    def forward(ctx, z_in, a_in, slope_in, W, bias, slope_out):
+        ac, Wc = _chk(a_in, "x"), _chk(W, "weight")
+        if ac.shape[-1] != Wc.shape[1]:
+            raise ValueError(f"gcl_b200: linear got x[..., {ac.shape[-1]}] and weight {tuple(Wc.shape)}")
+        bias_c = _chk(bias, "bias") if bias is not None else None
+        so = _chk(slope_out, "slope") if slope_out is not None else None
+        x2 = ac.view(-1, ac.shape[-1])
+        y, z = linear_fwd_raw(x2, Wc, bias_c, so, so is not None)
+        ctx.has_bias, ctx.has_act_in, ctx.lead = bias is not None, z_in is not None, ac.shape[:-1]
+        zi = _chk(z_in, "z_in").view(-1, ac.shape[-1]) if z_in is not None else None
+        si = _chk(slope_in, "slope_in") if z_in is not None else None
+        ctx.save_for_backward(x2, Wc, zi, si)
+        yv = y.view(*ac.shape[:-1], Wc.shape[0])
+        if so is None:
+            return yv
+        ctx.mark_non_differentiable(yv)
+        return z.view_as(yv), yv
+
+    @staticmethod
+    def backward(ctx, d, _da=None):
+        x2, W, zi, si = ctx.saved_tensors
+        d2 = _chk(d, "grad_out").view(-1, W.shape[0])
+        dz = dx = dsl = None
+        if ctx.has_act_in:
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[2]:
+                dz, dsl = linear_bwd_dx_prelu_raw(d2, W, zi, si)
+                dz, dsl = dz.view(*ctx.lead, W.shape[1]), dsl.view_as(si)
+        elif ctx.needs_input_grad[1]:
+            dx = linear_bwd_dx_raw(d2, W).view(*ctx.lead, W.shape[1])
+        dW = db = None
+        if ctx.needs_input_grad[3] or (ctx.has_bias and ctx.needs_input_grad[4]):
+            dW, db = linear_bwd_dw_raw(d2, x2, ctx.has_bias)
+        return dz, dx, dsl, dW, (db if ctx.has_bias else None), None
+
+
+def act_linear(z_in, a_in, slope_in, weight, bias=None, slope_out=None):
+    """See _ActLinear.  Returns y, or (z_out, a_out) when slope_out is given."""
+    return _ActLinear.apply(z_in, a_in, slope_in, weight, bias, slope_out)
 
 
 def linear(x, weight, bias=None, prelu_slope=None):

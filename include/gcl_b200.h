@@ -118,6 +118,13 @@ int gcl_linear_fwd_f32(const float* x, const float* W, const float* bias, float*
 /* dx[R, Cin] = dy[R, Cout] W.  wt_scratch: Cin*Cout floats (holds W^T for the tensor-core path). */
 int gcl_linear_bwd_dx_f32(const float* dy, const float* W, float* dx, int64_t rows, int64_t c_in,
                           int64_t c_out, float* wt_scratch, void* stream);
+/* Backward of "PReLU, then Linear" with respect to the PReLU's input z_in [rows, c_in] (the MLP of models.py:74-98
+ * alternates them): dz_in = (dy W) * PReLU'(z_in), *dslope = sum((dy W) * min(z_in, 0)).  One kernel on the
+ * tcgen05 path (epilogue of the dX GEMM); otherwise dX followed by an in-place PReLU backward. */
+size_t gcl_linear_bwd_dx_prelu_workspace_bytes(int64_t rows, int64_t c_in);
+int gcl_linear_bwd_dx_prelu_f32(const float* dy, const float* W, const float* z_in, const float* slope,
+                                float* dz_in, float* dslope, int64_t rows, int64_t c_in, int64_t c_out,
+                                float* wt_scratch, void* workspace, size_t workspace_bytes, void* stream);
 /* Which engine runs the dense transforms:
  *   GCL_DENSE_AUTO  tcgen05 tensor cores in 3xTF32 (hi/lo split, fp32 accumulate in TMEM; fp32-level
  *                   accuracy) when the shape fits (rows >= 2048, Cout <= 256), else FFMA   [default]

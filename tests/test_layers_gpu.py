@@ -239,6 +239,39 @@ def test_rows_concat_split_are_exact_and_inverse(B, na, nb, C):
     assert torch.equal(x.grad[:, na:], w[:, na:]) and not x.grad[:, :na].any()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,dims", [(3000, (72, 48, 48, 64)), (2500, (64, 128, 128, 64)), (300, (30, 48, 48, 33)),
+                                    (4100, (66, 96, 96, 96))])
+def test_mlp_chain_with_prelu_backward_fused_into_dx(R, dims):
+    """Linear+PReLU -> Linear+PReLU -> Linear differentiated through the pre-activations (ops.act_linear): the
+    PReLU backward runs in the epilogue of the next layer's dX kernel (tcgen05 path for R >= 2048, two-kernel
+    fallback below).  Checked against torch in fp64."""
+    from gcl_b200 import ops
+    g = torch.Generator().manual_seed(R + dims[1])
+    x = torch.randn(R, dims[0], generator=g)
+    Ws = [torch.randn(dims[i + 1], dims[i], generator=g) / dims[i] ** 0.5 for i in range(3)]
+    bs = [torch.randn(dims[i + 1], generator=g) * 0.1 for i in range(3)]
+    sl = [torch.tensor([0.25]), torch.tensor([0.1])]
+    w = torch.randn(R, dims[3], generator=g)
+
+    def leaves(dt, dev):
+        return [t.detach().clone().to(dev, dt).requires_grad_(True) for t in [x] + Ws + bs + sl]
+
+    L = leaves(torch.float64, "cpu")
+    h = torch.nn.functional.prelu(L[0] @ L[1].t() + L[4], L[7])
+    h = torch.nn.functional.prelu(h @ L[2].t() + L[5], L[8])
+    (((h @ L[3].t() + L[6]) * w.double()).sum()).backward()
+    P = leaves(torch.float32, DEV)
+    z1, a1 = ops.act_linear(None, P[0], None, P[1], P[4], P[7])
+    z2, a2 = ops.act_linear(z1, a1, P[7], P[2], P[5], P[8])
+    y = ops.act_linear(z2, a2, P[8], P[3], P[6])
+    assert not a1.requires_grad and z1.requires_grad
+    ((y * w.to(DEV)).sum()).backward()
+    names = ["x", "W1", "W2", "W3", "b1", "b2", "b3", "slope1", "slope2"]
+    for n, a, b in zip(names, P, L):
+        assert_close(a.grad, b.grad.float(), RTOL_F32, f"d{n}")
+
+
 def test_sparse_gat_subclass_and_prune():
     """The reference's SparseGATConv (models.py:112-151) restated on top of OUR GATConv: subclassing,
     super().forward(..., return_attention_weights=True), threshold mask; plus the fused prune kernel."""
