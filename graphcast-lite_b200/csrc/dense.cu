@@ -402,7 +402,8 @@ ColsumPlan colsum_plan(int64_t R) {
 namespace gcl {
 int umma_linear(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
                 const float* slope, float* z_out, cudaStream_t s, const float* z_in = nullptr,
-                const float* act_slope = nullptr, float* dslope_part = nullptr, int* n_parts = nullptr);
+                const float* act_slope = nullptr, float* dslope_part = nullptr, int* n_parts = nullptr,
+                const float* att = nullptr, float* sc_src = nullptr, float* sc_dst = nullptr);
                                                                      // umma_gemm.cu
 int umma_dw_splits(int64_t R, int64_t M, int64_t N);
 int umma_dw(const float* A, const float* B, float* part, float* part_colsum, int64_t R, int64_t M, int64_t N,
@@ -430,6 +431,36 @@ extern "C" int gcl_linear_fwd_f32(const float* x, const float* W, const float* b
   transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(W, wt_scratch, (int)c_out, (int)c_in);
   GCL_CHECK_LAUNCH("gcl_linear_fwd_f32(transpose)");
   return gemm_nn(x, wt_scratch, y, rows, c_out, c_in, bias, prelu_slope, z_out, s);
+}
+
+extern "C" int gcl_gat_scores_f32(const float* z, const float* att_src, const float* att_dst, float* a_src, float* a_dst,
+                                  int64_t rows, int64_t heads, int64_t c, void* stream);
+
+// y = x W^T (the bias-free `lin` of a single-head GATConv) together with the node terms of the attention logits,
+// a_src[r] = <y[r], att_src>, a_dst[r] = <y[r], att_dst>: one kernel on the tcgen05 path (GEMM epilogue), otherwise
+// the GEMM followed by gcl_gat_scores_f32.
+extern "C" int gcl_linear_fwd_scores_f32(const float* x, const float* W, float* y, const float* att_src,
+                                         const float* att_dst, float* a_src, float* a_dst, int64_t rows, int64_t c_in,
+                                         int64_t c_out, float* wt_scratch /* c_in*c_out + 2*c_out floats */,
+                                         void* stream) {
+  GCL_CHECK_ARG(x && W && y && att_src && att_dst && a_src && a_dst && wt_scratch,
+                "gcl_linear_fwd_scores_f32: null pointer argument");
+  GCL_CHECK_ARG(rows >= 0 && c_in > 0 && c_out > 0 && c_in <= 65536 && c_out <= 65536,
+                "gcl_linear_fwd_scores_f32: bad sizes");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rows == 0) return GCL_OK;
+  if (g_dense_mode != GCL_DENSE_FFMA && rows >= kUmmaMinRows) {
+    // the kernel wants [att_src ; att_dst] contiguous: pack them behind the transpose scratch
+    float* att = wt_scratch + c_in * c_out;
+    cudaMemcpyAsync(att, att_src, sizeof(float) * c_out, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(att + c_out, att_dst, sizeof(float) * c_out, cudaMemcpyDeviceToDevice, s);
+    const int rc = umma_linear(x, W, y, rows, c_out, c_in, nullptr, nullptr, nullptr, s, nullptr, nullptr, nullptr,
+                               nullptr, att, a_src, a_dst);
+    if (rc != GCL_ERR_UNSUPPORTED) return rc;
+  }
+  const int rc = gcl_linear_fwd_f32(x, W, nullptr, y, rows, c_in, c_out, nullptr, nullptr, wt_scratch, stream);
+  if (rc != GCL_OK) return rc;
+  return gcl_gat_scores_f32(y, att_src, att_dst, a_src, a_dst, rows, 1, c_out, stream);
 }
 
 extern "C" int gcl_linear_bwd_dx_f32(const float* dy, const float* W, float* dx, int64_t rows, int64_t c_in,

@@ -710,7 +710,11 @@ __global__ void __launch_bounds__(kLtThreads, 1)
                            int K, int n_pad, int nkb, int nob, int s_raw, int s_lo, int nbuf, int tmem_cols, int has_z,
                            const float* __restrict__ bias, const float* __restrict__ prelu_slope, int n_split,
                            const __grid_constant__ CUtensorMap tmZin, const float* __restrict__ act_slope,
-                           float* __restrict__ dslope_part) {
+                           float* __restrict__ dslope_part, const float* __restrict__ att,
+                           float* __restrict__ sc_src, float* __restrict__ sc_dst) {
+  // att != nullptr (the `lin` of a single-head GATConv): the epilogue also produces the attention logits' node
+  // terms sc_src[row] = <y[row], att[0:N]>, sc_dst[row] = <y[row], att[N:2N]> (models.py:336-357 via PyG's
+  // (x * att).sum(-1)), which otherwise costs a second pass over y.
   // act_slope != nullptr (used for dX): the result is multiplied by PReLU'(z_in) of the layer that produced this
   // layer's input, z_in tiles arrive by TMA like A, and sum(result * min(z_in, 0)) -- that PReLU's slope
   // gradient -- leaves as one partial per CTA.  Saves the separate pass over dX, z_in and dZ.
@@ -733,7 +737,9 @@ __global__ void __launch_bounds__(kLtThreads, 1)
   const int out_buf_bytes = (1 + has_z) * nob * kSlabBytes;
   uint8_t* zin = c_out + (size_t)nbuf * out_buf_bytes;                 // [nob] slabs of z_in, single-buffered
   float* bias_s = reinterpret_cast<float*>(zin + (size_t)(has_act ? nob : 0) * kSlabBytes);
-  uint64_t* bar_ptr = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bias_s + n_pad) + 15) & ~uintptr_t(15));
+  float* att_s = bias_s + n_pad;                                       // [2][n_pad]
+  float* sc_part = att_s + 2 * n_pad;                                  // [2 tiles][2 column groups][128 rows][2]
+  uint64_t* bar_ptr = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sc_part + 2 * 2 * kTileM * 2) + 15) & ~uintptr_t(15));
   const uint32_t bars = smem_u32(bar_ptr);
   const int kRawFull = 0, kRawEmpty = s_raw, kLoFull = 2 * s_raw, kLoEmpty = 2 * s_raw + s_lo,
             kAccFull = 2 * s_raw + 2 * s_lo, kAccEmpty = kAccFull + 2;
@@ -772,6 +778,10 @@ __global__ void __launch_bounds__(kLtThreads, 1)
     split_store(b_hi + (size_t)kb * b_block, b_lo + (size_t)kb * b_block, sw_off(n, c), v);
   }
   for (int n = tid; n < n_pad; n += kLtThreads) bias_s[n] = (bias && n < N) ? __ldg(bias + n) : 0.f;
+  for (int n = tid; n < 2 * n_pad; n += kLtThreads) {
+    const int which = n / n_pad, c = n % n_pad;
+    att_s[n] = (att && c < N) ? __ldg(att + which * N + c) : 0.f;
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -878,6 +888,7 @@ __global__ void __launch_bounds__(kLtThreads, 1)
       if (has_act) mbar_wait(bar(kZinFull), (uint32_t)(t_local & 1));
       const bool row_ok = tile * kTileM + my < M;          // rows past M hold zero-filled z_in: keep them out of dsl
       const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * 2 * n_pad);
+      float ps = 0.f, pd = 0.f;
       for (int c0 = cgrp * 16; c0 < n_pad; c0 += 32) {
         float v[16], vc[16];
         tmem_ld16x2(taddr + c0, taddr + n_pad + c0, v, vc);
@@ -888,6 +899,11 @@ __global__ void __launch_bounds__(kLtThreads, 1)
           const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col);
           float4 o = make_float4((v[4 * q] + vc[4 * q]) + b4.x, (v[4 * q + 1] + vc[4 * q + 1]) + b4.y,
                                  (v[4 * q + 2] + vc[4 * q + 2]) + b4.z, (v[4 * q + 3] + vc[4 * q + 3]) + b4.w);
+          if (att) {
+            const float4 s4 = *reinterpret_cast<const float4*>(att_s + col), d4 = *reinterpret_cast<const float4*>(att_s + n_pad + col);
+            ps += (o.x * s4.x + o.y * s4.y) + (o.z * s4.z + o.w * s4.w);
+            pd += (o.x * d4.x + o.y * d4.y) + (o.z * d4.z + o.w * d4.w);
+          }
           if (has_act) {
             const float4 zv = *reinterpret_cast<const float4*>(zin + off);
             if (row_ok && col < N)
@@ -902,11 +918,20 @@ __global__ void __launch_bounds__(kLtThreads, 1)
           *reinterpret_cast<float4*>(ob + off) = o;
         }
       }
+      float* scp = sc_part + (size_t)(t_local & 1) * (2 * kTileM * 2);
+      if (att) {
+        scp[(cgrp * kTileM + my) * 2] = ps;
+        scp[(cgrp * kTileM + my) * 2 + 1] = pd;
+      }
       tc_fence_before();
       mbar_arrive(bar(kAccEmpty + acc));
       fence_proxy_async();
       if (nbuf == 2 && tid == 0) bulk_wait_read();
       named_bar(1, kLtEpiThreads);
+      if (att && cgrp == 0 && row_ok) {                    // column group 0 + 1, fixed order
+        sc_src[tile * kTileM + my] = scp[my * 2] + scp[(kTileM + my) * 2];
+        sc_dst[tile * kTileM + my] = scp[my * 2 + 1] + scp[(kTileM + my) * 2 + 1];
+      }
       if (tid == 0) {
         if (has_act && tile + ncta < ntiles) fetch_zin(tile + ncta);   // everyone has read this tile's z_in
         for (int j = 0; j < nob; ++j) {
@@ -1227,7 +1252,7 @@ TmaLinPlan plan_linear_tma(int64_t N, int64_t K, bool has_z, bool has_act = fals
   p.nob = (int)((N + kKB - 1) / kKB);
   if (N < kKB || K < kKB || p.n_pad > 256 || (N & 3) || (K & 3)) return p;
   const long w_bytes = 2L * p.nkb * p.n_pad * 128;
-  const long fixed = 1024 + 512 + 4L * p.n_pad;
+  const long fixed = 1024 + 512 + 4L * p.n_pad * 3 + 4L * 2 * 2 * kTileM * 2;   // bias, att, score partials
   long slabs = 0, out_bytes = 0;
   for (p.nbuf = 2; p.nbuf >= 1; --p.nbuf) {       // two output buffers if at least 7 operand slabs remain
     out_bytes = (long)p.nbuf * p.nob * kSlabBytes * (has_z ? 2 : 1) + (has_act ? (long)p.nob * kSlabBytes : 0);
@@ -1250,7 +1275,7 @@ TmaLinPlan plan_linear_tma(int64_t N, int64_t K, bool has_z, bool has_act = fals
 
 int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
                     const float* slope, float* z_out, const float* z_in, const float* act_slope, float* dslope_part,
-                    int* n_parts, cudaStream_t s) {
+                    int* n_parts, const float* att, float* sc_src, float* sc_dst, cudaStream_t s) {
   if (act_slope && (!z_in || !dslope_part || !al16(z_in) || z_out)) return GCL_ERR_UNSUPPORTED;
   if (!(al16(A) && al16(W_nk) && al16(C) && (!z_out || al16(z_out))) || M <= 0 || M > 0x7fffff00LL)
     return GCL_ERR_UNSUPPORTED;
@@ -1260,7 +1285,7 @@ int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int6
     p = plan_linear_tma(N / 2, K, z_out != nullptr, act_slope != nullptr);
     n_split = 2;
   }
-  if (!p.ok) return GCL_ERR_UNSUPPORTED;
+  if (!p.ok || (att && n_split != 1)) return GCL_ERR_UNSUPPORTED;
   CUtensorMap tmA, tmC, tmZ, tmZin;
   if (!make_map_2d(&tmA, A, M, K, kTileM, kKB, CU_TENSOR_MAP_SWIZZLE_128B) ||
       !make_map_2d(&tmC, C, M, N, kTileM, kKB, CU_TENSOR_MAP_SWIZZLE_128B) ||
@@ -1276,7 +1301,7 @@ int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int6
   umma_linear_tma_kernel<<<grid, kLtThreads, p.smem, s>>>(tmA, tmC, tmZ, W_nk, M, (int)(N / n_split), (int)K, p.n_pad,
                                                           p.nkb, p.nob, p.s_raw, p.s_lo, p.nbuf, p.tmem_cols,
                                                           z_out ? 1 : 0, bias, slope, n_split, tmZin, act_slope,
-                                                          dslope_part);
+                                                          dslope_part, att, sc_src, sc_dst);
   if (n_parts) *n_parts = grid;
   GCL_CHECK_LAUNCH("umma_linear_tma");
   return GCL_OK;
@@ -1287,13 +1312,15 @@ int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int6
 // the FFMA kernel), or an error.
 int umma_linear(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
                 const float* slope, float* z_out, cudaStream_t s, const float* z_in, const float* act_slope,
-                float* dslope_part, int* n_parts) {
-  if (act_slope) {   // only the TMA kernel has the fused PReLU-backward epilogue
+                float* dslope_part, int* n_parts, const float* att, float* sc_src, float* sc_dst) {
+  if (act_slope || att) {   // only the TMA kernel has the fused PReLU-backward / attention-score epilogues
     if (g_force_register_staging) return GCL_ERR_UNSUPPORTED;
-    return umma_linear_tma(A, W_nk, C, M, N, K, bias, slope, z_out, z_in, act_slope, dslope_part, n_parts, s);
+    return umma_linear_tma(A, W_nk, C, M, N, K, bias, slope, z_out, z_in, act_slope, dslope_part, n_parts, att, sc_src,
+                           sc_dst, s);
   }
   if (!g_force_register_staging) {
-    const int rc = umma_linear_tma(A, W_nk, C, M, N, K, bias, slope, z_out, nullptr, nullptr, nullptr, nullptr, s);
+    const int rc = umma_linear_tma(A, W_nk, C, M, N, K, bias, slope, z_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                   nullptr, s);
     if (rc != GCL_ERR_UNSUPPORTED) return rc;
   }
   LinPlan p = plan_linear(N, K, z_out != nullptr, al16(C) && (!z_out || al16(z_out)));

@@ -22,6 +22,7 @@ _PROTOS = {
     "gcl_csr_weights": (c_int, [P, P, P, P, P, I64, I64, I32, P, P, P, P]),
     "gcl_spmm_f32": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "gcl_linear_fwd_f32": (c_int, [P, P, P, P, I64, I64, I64, P, P, P, P]),
+    "gcl_linear_fwd_scores_f32": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, P, P]),
     "gcl_linear_bwd_dx_f32": (c_int, [P, P, P, I64, I64, I64, P, P]),
     "gcl_linear_bwd_dx_prelu_workspace_bytes": (c_size_t, [I64, I64]),
     "gcl_linear_bwd_dx_prelu_f32": (c_int, [P, P, P, P, P, P, I64, I64, I64, P, P, c_size_t, P]),

@@ -159,9 +159,9 @@ class GraphLayer(nn.Module):
             elif type(m) is GATConv:
                 if fuse and m.heads == 1:                    # GATConv + the shared PReLU in one aggregation kernel
                     g = GLOBAL_CACHE.get(edge_index, n, CSR_LOOPS if m.add_self_loops else CSR_RAW)
-                    z = ops.linear(X, m.lin.weight)
+                    z, a_s, a_d = ops.linear_scores(X, m.lin.weight, m.att_src, m.att_dst)
                     X, _ = ops.gat_attend(z, m.att_src, m.att_dst, m.bias, g, 1, m.concat, m.negative_slope,
-                                          prelu_slope=nxt.weight)
+                                          prelu_slope=nxt.weight, scores=(a_s, a_d))
                     i += 2
                 else:
                     X = m(X, edge_index)

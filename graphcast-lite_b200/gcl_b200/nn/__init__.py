@@ -140,10 +140,15 @@ class GATConv(MessagePassing):
             raise NotImplementedError("gcl_b200.GATConv: edge_attr / size are not used by graphcast-lite")
         mode = CSR_LOOPS if self.add_self_loops else CSR_RAW
         g = GLOBAL_CACHE.get(edge_index, _num_nodes(x), mode)
-        z = ops.linear(x, self.lin.weight)
         want = isinstance(return_attention_weights, bool)
+        scores = None
+        if self.heads == 1:              # logits' node terms from the epilogue of the `lin` GEMM
+            z, a_s, a_d = ops.linear_scores(x, self.lin.weight, self.att_src, self.att_dst)
+            scores = (a_s, a_d)
+        else:
+            z = ops.linear(x, self.lin.weight)
         out, alpha = ops.gat_attend(z, self.att_src, self.att_dst, self.bias, g, self.heads, self.concat,
-                                    self.negative_slope, want_alpha=want)
+                                    self.negative_slope, want_alpha=want, scores=scores)
         if want:
             return out, (g.edge_index_with_loops, alpha)
         return out

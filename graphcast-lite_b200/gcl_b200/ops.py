@@ -317,6 +317,53 @@ def act_linear(z_in, a_in, slope_in, weight, bias=None, slope_out=None):
     return _ActLinear.apply(z_in, a_in, slope_in, weight, bias, slope_out)
 
 
+class _LinearScores(torch.autograd.Function):
+    """z = x W^T plus the attention logits' node terms (z * att).sum(-1) of a single-head GATConv, one kernel.
+    The scores are returned as non-differentiable buffers: their gradient path (d att, and the part of dz that
+    comes through them) is produced by the GAT backward, which owns the scores."""
+
+    @staticmethod
+    def forward(ctx, x, W, att_src, att_dst):
+        xc, Wc = _chk(x, "x"), _chk(W, "weight")
+        if xc.shape[-1] != Wc.shape[1]:
+            raise ValueError(f"gcl_b200: linear got x[..., {xc.shape[-1]}] and weight {tuple(Wc.shape)}")
+        a_s, a_d = _chk(att_src, "att_src").view(-1), _chk(att_dst, "att_dst").view(-1)
+        cout, cin = Wc.shape
+        if a_s.numel() != cout or a_d.numel() != cout:
+            raise ValueError("gcl_b200: linear_scores is for heads == 1 (att vectors of out_channels elements)")
+        x2 = xc.view(-1, cin)
+        R = x2.shape[0]
+        dev = x2.device
+        z = torch.empty((R, cout), dtype=torch.float32, device=dev)
+        asrc = torch.empty(R, dtype=torch.float32, device=dev)
+        adst = torch.empty(R, dtype=torch.float32, device=dev)
+        wt = torch.empty(cin * cout + 2 * cout, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _call("gcl_linear_fwd_scores_f32", _p(x2), _p(Wc), _p(z), _p(a_s), _p(a_d), _p(asrc), _p(adst), R, cin, cout,
+                  _p(wt), _stream(), nbytes=4 * R * (cin + cout + 2) + 4 * cin * cout, tag=f"R{R}x{cin}->{cout}")
+        ctx.save_for_backward(x2, Wc)
+        lead = xc.shape[:-1]
+        asrc, adst = asrc.view(*lead, 1), adst.view(*lead, 1)
+        ctx.mark_non_differentiable(asrc, adst)
+        return z.view(*lead, cout), asrc, adst
+
+    @staticmethod
+    def backward(ctx, dz, _ds=None, _dd=None):
+        x2, W = ctx.saved_tensors
+        d2 = _chk(dz, "grad_out").view(-1, W.shape[0])
+        dx = dW = None
+        if ctx.needs_input_grad[0]:
+            dx = linear_bwd_dx_raw(d2, W).view(*dz.shape[:-1], W.shape[1])
+        if ctx.needs_input_grad[1]:
+            dW, _ = linear_bwd_dw_raw(d2, x2, False)
+        return dx, dW, None, None
+
+
+def linear_scores(x, weight, att_src, att_dst):
+    """(z, a_src, a_dst) for a single-head GATConv: pass the scores on to gat_attend(scores=...)."""
+    return _LinearScores.apply(x, weight, att_src, att_dst)
+
+
 def linear(x, weight, bias=None, prelu_slope=None):
     return _Linear.apply(x, weight, bias, prelu_slope)
 
@@ -391,7 +438,8 @@ class _GAT(torch.autograd.Function):
     z is the already-transformed [B, N, H*C] (or [N, H*C]) feature matrix."""
 
     @staticmethod
-    def forward(ctx, z, att_src, att_dst, bias, graph: CSRGraph, heads, concat, slope, want_alpha, prelu_slope=None):
+    def forward(ctx, z, att_src, att_dst, bias, graph: CSRGraph, heads, concat, slope, want_alpha, prelu_slope=None,
+                scores=None):
         z3, squeeze = _as3(_chk(z, "z"))
         if prelu_slope is not None and int(heads) != 1:
             raise NotImplementedError("gcl_b200: PReLU fused into GATConv needs heads == 1")
@@ -402,8 +450,11 @@ class _GAT(torch.autograd.Function):
         a_s, a_d = _chk(att_src, "att_src").view(-1), _chk(att_dst, "att_dst").view(-1)
         bias_c = _chk(bias, "bias") if bias is not None else None
         dev = z3.device
-        asrc = torch.empty((B, N, H), dtype=torch.float32, device=dev)
-        adst = torch.empty((B, N, H), dtype=torch.float32, device=dev)
+        if scores is not None:           # produced by the epilogue of the `lin` GEMM (ops.linear_scores)
+            asrc, adst = (_chk(t, "scores").view(B, N, H) for t in scores)
+        else:
+            asrc = torch.empty((B, N, H), dtype=torch.float32, device=dev)
+            adst = torch.empty((B, N, H), dtype=torch.float32, device=dev)
         nnz = graph.nnz
         cout = HC if concat else C
         out = torch.empty((B, N, cout), dtype=torch.float32, device=dev)
@@ -411,8 +462,9 @@ class _GAT(torch.autograd.Function):
         alpha_pyg = torch.empty((B, max(nnz, 1), H), dtype=torch.float32, device=dev) if want_alpha else None
         zpre = torch.empty_like(out) if ps is not None else None
         with torch.cuda.device(dev):
-            _call("gcl_gat_scores_f32", _p(z3), _p(a_s), _p(a_d), _p(asrc), _p(adst), B * N, H, C, _stream(),
-                  nbytes=4 * B * N * (H * C + 2 * H), tag=f"R{B * N}xH{H}xC{C}")
+            if scores is None:
+                _call("gcl_gat_scores_f32", _p(z3), _p(a_s), _p(a_d), _p(asrc), _p(adst), B * N, H, C, _stream(),
+                      nbytes=4 * B * N * (H * C + 2 * H), tag=f"R{B * N}xH{H}xC{C}")
             _call("gcl_gat_fwd_f32", _p(graph.rowptr), _p(graph.col), _p(graph.perm), _p(z3), _p(asrc), _p(adst),
                   _p(bias_c), _p(out), _p(alpha), _p(alpha_pyg), _p(ps), _p(zpre), B, N, nnz, H, C, int(bool(concat)),
                   float(slope),
@@ -461,12 +513,14 @@ class _GAT(torch.autograd.Function):
         dbias = colsum_raw(d3.view(-1, d3.shape[-1])) if ctx.has_bias else None
         if ctx.squeeze:
             dz = dz.squeeze(0)
-        return dz, datt_s.view(1, H, C), datt_d.view(1, H, C), dbias, None, None, None, None, None, dslope
+        return dz, datt_s.view(1, H, C), datt_d.view(1, H, C), dbias, None, None, None, None, None, dslope, None
 
 
-def gat_attend(z, att_src, att_dst, bias, graph, heads, concat, negative_slope, want_alpha=False, prelu_slope=None):
-    """prelu_slope (heads == 1): PReLU applied behind the bias inside the aggregation kernel."""
-    return _GAT.apply(z, att_src, att_dst, bias, graph, heads, concat, negative_slope, want_alpha, prelu_slope)
+def gat_attend(z, att_src, att_dst, bias, graph, heads, concat, negative_slope, want_alpha=False, prelu_slope=None,
+               scores=None):
+    """prelu_slope (heads == 1): PReLU applied behind the bias inside the aggregation kernel.
+    scores = (a_src, a_dst) from linear_scores(): skips the separate score pass over z."""
+    return _GAT.apply(z, att_src, att_dst, bias, graph, heads, concat, negative_slope, want_alpha, prelu_slope, scores)
 
 
 def _rows_concat_raw(a, b, B, na, nb, C, dev):

@@ -116,6 +116,11 @@ int gcl_linear_fwd_f32(const float* x, const float* W, const float* bias, float*
                        int64_t c_in, int64_t c_out, const float* prelu_slope, float* z_out,
                        float* wt_scratch, void* stream);
 /* dx[R, Cin] = dy[R, Cout] W.  wt_scratch: Cin*Cout floats (holds W^T for the tensor-core path). */
+/* `lin` of a single-head GATConv together with the node terms of the attention logits (PyG: (x * att).sum(-1)):
+ * y = x W^T, a_src[r] = <y[r], att_src>, a_dst[r] = <y[r], att_dst>; wt_scratch: c_in*c_out + 2*c_out floats. */
+int gcl_linear_fwd_scores_f32(const float* x, const float* W, float* y, const float* att_src,
+                              const float* att_dst, float* a_src, float* a_dst, int64_t rows, int64_t c_in,
+                              int64_t c_out, float* wt_scratch, void* stream);
 int gcl_linear_bwd_dx_f32(const float* dy, const float* W, float* dx, int64_t rows, int64_t c_in,
                           int64_t c_out, float* wt_scratch, void* stream);
 /* Backward of "PReLU, then Linear" with respect to the PReLU's input z_in [rows, c_in] (the MLP of models.py:74-98
