@@ -5,11 +5,17 @@
 //   e_ij   = LeakyReLU(a_src[j] + a_dst[i])                      (j -> i, self loops included)
 //   alpha  = exp(e - max_i) / (sum_i exp(.) + 1e-16)             (torch_geometric.utils.softmax)
 //   out_i  = mean_h / concat_h ( sum_j alpha_ijh z_jh ) + bias
-// One warp owns one (sample, receiver).  The 32 lanes first run over the receiver's incoming edges
-// (max, sum, alpha: segment softmax with warp shuffles), then switch to "S slots x L lanes": each slot
-// gathers a different neighbour row, L lanes each hold one 128-bit word of the C-wide head slice, and
-// the slots are folded with a fixed-order shuffle tree.  alpha is written once in CSR order (kept for
-// backward) and optionally scattered to PyG edge order (return_attention_weights / pruning).
+// Mapping (all three aggregate kernels): a group of L lanes (L = 4..32 128-bit words of a head slice) owns one
+// (receiver or sender row, SB samples), 32/L groups share a warp; lane k of the group also holds edge k of the row,
+// so per-row scalars (logits, softmax, alpha) live one edge per lane and are broadcast by group shuffles while
+// every lane gathers its word of each neighbour row for SB samples.
+//   heads == 1 forward : gat_alpha_kernel (coefficients, thread per (sample, row)) + the SpMM kernel with
+//                        per-sample weights (spmm.cu), bias and optionally the layer's PReLU in its epilogue
+//   heads  > 1 forward : gat_fwd_kernel (fused logits / softmax / aggregate / head mean or concat)
+//   backward           : gat_bwd_dst_kernel (d alpha by a butterfly transpose-reduce of the edge dot products,
+//                        softmax backward, da_dst) then gat_bwd_src_kernel on the sender-grouped CSR (dz, da_src)
+// alpha is written once in CSR order (kept for backward) and optionally scattered to PyG edge order
+// (return_attention_weights / pruning).
 #include "common.cuh"
 #include "scan.cuh"
 

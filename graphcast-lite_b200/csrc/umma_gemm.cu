@@ -1,19 +1,22 @@
 // K7 on the 5th-generation tensor cores: fp32-accurate dense transforms with tcgen05 (UMMA) in
-// 3xTF32 -- every fp32 operand is split into hi = tf32(x) and lo = tf32(x - hi) and
-//     D += A_hi B_hi + A_lo B_hi + A_hi B_lo           (fp32 accumulation in TMEM)
+// 3xTF32 -- every fp32 operand is split into hi (tf32) and lo = x - hi and
+//     D = A_hi B_hi + (A_lo B_hi + A_hi B_lo)           (fp32 accumulation in TMEM)
 // which keeps ~22 mantissa bits per product, enough for the rel 1e-4 parity bar that plain TF32 (10
-// bits) misses (DESIGN.md "dense transform").  The split is why operands are staged by ordinary loads +
-// st.shared instead of TMA: the loader warps convert while they copy, writing the UMMA canonical
-// 128-byte-swizzled layouts directly.
+// bits) misses (DESIGN.md "Dense transform").
 //
-//   umma_linear_kernel : C[M,N] = A[M,K] W[N,K]^T (+bias, PReLU, pre-activation copy)
-//                        forward of nn.Linear / PyG lin (W = weight) and dX = dY W (W = weight^T)
-//   umma_dw_kernel     : P[s][N1,N2] = sum_{r in slice s} A[r,N1]^T B[r,N2]   (dW = dY^T X partials)
+//   umma_linear_tma_kernel : C[M,N] = A[M,K] W[N,K]^T (+bias, PReLU, pre-activation copy; or the PReLU-backward
+//                            epilogue for dX; or the attention-score epilogue of GATConv's lin).  TMA tensor
+//                            loads feed the hi operand directly (hi = trunc), converter warps write lo, the
+//                            corrections accumulate in their own TMEM accumulator, TMA tensor stores.  Default.
+//   umma_dw_tma_kernel     : P[s][N1,N2] = sum_{r in slice s} A[r,N1]^T B[r,N2] (dW = dY^T X partials): TMA loads
+//                            raw row blocks, converter warps transpose + split them into K-major stages.  Default.
+//   umma_linear_kernel, umma_dw_kernel : the register-staged first generation (loader warps ld.global -> split ->
+//                            st.shared).  Kept for rows that are not 16-byte aligned (TMA cannot address them)
+//                            and as the A/B switch GCL_UMMA_NO_TMA=1.
 //
-// Persistent, warp-specialised CTAs (one per SM): warps 0-3 epilogue (TMEM -> registers -> global; a
-// warp may only touch TMEM lanes 32*(warp%4)..+31), warp 4 allocates TMEM and its lane 0 issues the
-// MMAs, warps 5-11 load/split/stage.  mbarrier rings: full/empty per smem stage, full/empty per TMEM
-// accumulator (two accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1).
+// All are persistent, warp-specialised CTAs (one per SM): a warp may only touch TMEM lanes 32*(warp%4)..+31, so
+// epilogue warps come in groups of four; one warp allocates TMEM and one elected lane issues the MMAs; mbarrier
+// rings per smem stage and per TMEM accumulator (two, so the epilogue of tile i overlaps the MMAs of tile i+1).
 #include <cuda.h>   // CUtensorMap types only; the encoder is resolved at run time
 
 #include "common.cuh"
@@ -148,15 +151,8 @@ __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, 
   *reinterpret_cast<float4*>(lo_base + off) = l;
 }
 
-// UMMA shared-memory descriptor, 128-byte swizzle, version 1 (sm_100): start address, LBO, SBO in 16 B
-// units (cute::UMMA::SmemDescriptor bit layout).
-// layout: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout tcgen05 accepts for
-// MN-major tf32 operands: 32-byte chunks of a 128-byte row XORed with row % 4, atoms of 4 rows).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint64_t layout = 2) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
-}
+// UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor bit layout, version 1 = sm_100): start address,
+// LBO, SBO in 16-byte units, layout 2 = SWIZZLE_128B for K-major operands -- built by desc_lo / desc_k128 below.
 // The MMA-issuing warp is a single instruction stream, and ncu showed it -- not DRAM, not the tensor core --
 // pacing the kernels when every MMA rebuilt its descriptors and ring indices with divisions.  So: the K-major
 // SWIZZLE_128B descriptor is split into a constant high word and a low word (address >> 4 | LBO) that advances
@@ -685,9 +681,6 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 __device__ __forceinline__ float lo_trunc(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 constexpr int kSlabBytes = kTileM * 128;     // [128 rows x 32 fp32], 16 KB
-constexpr int kConvWarps = 6;                // warps 6..11
-constexpr int kConvThreads = kConvWarps * 32;
-constexpr int kDwConvWarps = kConvWarps + kEpiWarps;   // dW: the epilogue warps convert too until the last MMA
 __device__ __forceinline__ float lds_f32(uint32_t a) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
