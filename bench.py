@@ -324,6 +324,7 @@ def run_gcl(args):
                     "h2d_bytes_per_step": world * int(hx.numel() + hy.numel()) * 4, "d2h_bytes_per_step": world * 4,
                     "api": "gcl_b200.train.Trainer.step_from_host(X_pinned, y_pinned, next_batch) -> float loss; "
                            "the next batch's H2D copy runs on a copy stream during the step"},
+            "hbm_peak_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2),
             "gpu_launches": int(tr.launches_in_graph * args.steps + eager_launches),
             "gpu_launches_per_step": int(tr.launches_in_graph + eager_launches // max(args.steps, 1)),
             "loss": last_loss,
