@@ -272,6 +272,32 @@ def test_mlp_chain_with_prelu_backward_fused_into_dx(R, dims):
         assert_close(a.grad, b.grad.float(), RTOL_F32, f"d{n}")
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,B", [(64, 3), (36, 2), (33, 1)])
+def test_aggregate_restricted_to_a_row_prefix(C, B):
+    """rows_out = n (the decoder keeps only its grid rows, models.py:852): forward equals the full aggregation
+    sliced, and the backward -- a [B, n, C] gradient read through the transposed CSR with n_rows_in masking --
+    equals the backward of the sliced full result."""
+    from gcl_b200 import ops
+    from gcl_b200.graph import CSR_LOOPS, NORM_GCN, CSRGraph
+    n, keep = 700, 180
+    ei = random_graph(n, 5000, seed=C, heavy=60, self_loops=4, dups=5, isolated=15).to(DEV)
+    g = CSRGraph(ei, n, CSR_LOOPS)
+    gen = torch.Generator().manual_seed(C + B)
+    x1 = torch.randn(B, n, C, generator=gen).to(DEV).requires_grad_(True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    bias = torch.randn(C, generator=gen).to(DEV)
+    slope = torch.tensor([0.2], device=DEV)
+    w = torch.randn(B, keep, C, generator=gen).to(DEV)
+    part = ops.aggregate(x1, g, NORM_GCN, bias, slope, rows_out=keep)
+    full = ops.aggregate(x2, g, NORM_GCN, bias, slope)
+    assert part.shape == (B, keep, C)
+    assert torch.equal(part, full[:, :keep])
+    (part * w).sum().backward()
+    (full[:, :keep] * w).sum().backward()
+    assert_close(x1.grad, x2.grad, 1e-6, "dx through the row-prefix aggregation")
+
+
 def test_sparse_gat_subclass_and_prune():
     """The reference's SparseGATConv (models.py:112-151) restated on top of OUR GATConv: subclassing,
     super().forward(..., return_attention_weights=True), threshold mask; plus the fused prune kernel."""
