@@ -14,6 +14,7 @@ Product graph, InteractionNet and regional meshes are out of scope
 from typing import Optional
 
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -73,7 +74,8 @@ class MLP(nn.Module):
 
 
 class SparseGATConv(GATConv):
-    """models.py:112-151.  For B > 1 the pruning decision uses the batch-mean attention."""
+    """models.py:112-151.  For B > 1 the pruning decision uses the batch-mean attention (over the global batch when
+    data-parallel, so every replica prunes to the same graph)."""
 
     def __init__(self, in_channels, out_channels, heads=1, concat=False, dropout=0.0, bias=True, **kw):
         super().__init__(in_channels, out_channels, heads, concat=concat, dropout=dropout, bias=bias, **kw)
@@ -85,6 +87,12 @@ class SparseGATConv(GATConv):
             att = att.mean(dim=0)
         att = att.squeeze()
         if batch_num == 0:
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                # data-parallel replicas must keep the SAME edge set: prune on the attention averaged over the
+                # global batch (the reference is single-process, models.py:140-149)
+                att = att.contiguous()
+                dist.all_reduce(att, op=dist.ReduceOp.SUM)
+                att = att / dist.get_world_size()
             edge_index = ops.edge_prune(edge_index, att, float(attention_threshold))
         return out, (edge_index, att)
 
