@@ -263,6 +263,22 @@ def run_gcl(args):
     barrier()
     clocks = sampler.stop()
 
+    # ---- inference: forecast steps without autograd (eager launches), device-resident inputs
+    infer = None
+    if rank == 0:
+        with torch.no_grad():
+            for _ in range(3):
+                model(X=tr.static_x)
+            n_inf = max(args.steps, 5)
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            i0.record()
+            for _ in range(n_inf):
+                model(X=tr.static_x)
+            i1.record()
+            torch.cuda.synchronize(dev)
+        infer = {"value": B / (i0.elapsed_time(i1) / n_inf * 1e-3), "unit": "forecast samples/s (forward only, one GPU)",
+                 "ms_per_step": i0.elapsed_time(i1) / n_inf}
+
     # ---- per-kernel CUDA-event timing inside real (eager) steps: roofline of the dominant kernel
     peak, peak_src = measured_peak_gbs()
     roof, by_kernel, edges = None, [], None
@@ -304,6 +320,11 @@ def run_gcl(args):
                          "edges_per_s": B * nnz / (a["ms"] / a["calls"] * 1e-3),
                          "algo_GBps": a["bytes"] / (a["ms"] * 1e-3) / 1e9,
                          "frac_hbm": a["bytes"] / (a["ms"] * 1e-3) / 1e9 / peak}
+                # forward + backward of one processor layer: the GAT backward entry, or (GCN) the same SpMM entry,
+                # which is called once forward and once backward per layer (its average covers both directions)
+                bwd = agg.get(("gcl_gat_bwd_f32", tag))
+                t_fb = (a["ms"] / a["calls"] + bwd["ms"] / bwd["calls"]) if bwd else 2 * a["ms"] / a["calls"]
+                edges["fwd_bwd_edges_per_s"] = B * nnz / (t_fb * 1e-3)
                 break
 
     if rank == 0:
@@ -328,7 +349,7 @@ def run_gcl(args):
             "gpu_launches": int(tr.launches_in_graph * args.steps + eager_launches),
             "gpu_launches_per_step": int(tr.launches_in_graph + eager_launches // max(args.steps, 1)),
             "loss": last_loss,
-            "roofline": roof, "kernels": by_kernel, "mesh_message_passing": edges,
+            "roofline": roof, "kernels": by_kernel, "mesh_message_passing": edges, "inference": infer,
             "cpu_baseline": cpu_base,
         }
         print(json.dumps(out), flush=True)
