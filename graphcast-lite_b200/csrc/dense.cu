@@ -407,7 +407,7 @@ int umma_linear(const float* A, const float* W_nk, float* C, int64_t M, int64_t 
                                                                      // umma_gemm.cu
 int umma_dw_splits(int64_t R, int64_t M, int64_t N);
 int umma_dw(const float* A, const float* B, float* part, float* part_colsum, int64_t R, int64_t M, int64_t N,
-            cudaStream_t s);
+            cudaStream_t s, int* n_bias_parts);
 static int g_dense_mode = GCL_DENSE_AUTO;
 constexpr int64_t kUmmaMinRows = 2048;   // below this the FFMA kernel's many small CTAs win
 }  // namespace gcl
@@ -543,7 +543,7 @@ extern "C" size_t gcl_linear_bwd_dw_workspace_bytes(int64_t rows, int64_t c_in, 
   int nsplit = pl.nsplit;
   const int us = umma_dw_splits(rows, c_out, c_in);
   if (us > nsplit) nsplit = us;
-  return (size_t)nsplit * (size_t)(c_out * c_in + c_out) * sizeof(float) + 256;
+  return (size_t)nsplit * (size_t)(c_out * c_in + 16 * c_out) * sizeof(float) + 256;   // + bias partials (<= 16 per slice)
 }
 
 extern "C" int gcl_linear_bwd_dw_f32(const float* dy, const float* x, float* dW, float* dbias, int64_t rows,
@@ -568,12 +568,13 @@ extern "C" int gcl_linear_bwd_dw_f32(const float* dy, const float* x, float* dW,
     const int us = umma_dw_splits(rows, M, N);
     if (us > 0) {
       float* upcs = part + (size_t)us * M * N;
-      const int rc = umma_dw(dy, x, part, dbias ? upcs : nullptr, rows, M, N, s);
+      int nbp = us;
+      const int rc = umma_dw(dy, x, part, dbias ? upcs : nullptr, rows, M, N, s, &nbp);
       if (rc != GCL_OK) return rc;
       reduce_partials_kernel<<<(unsigned)ceil_div((int64_t)M * N, 32), dim3(32, 32), 0, s>>>(part, dW, (int64_t)M * N, us);
       GCL_CHECK_LAUNCH("gcl_linear_bwd_dw_f32(reduce)");
       if (dbias) {
-        reduce_partials_kernel<<<(unsigned)ceil_div(M, 32), dim3(32, 32), 0, s>>>(upcs, dbias, M, us);
+        reduce_partials_kernel<<<(unsigned)ceil_div(M, 32), dim3(32, 32), 0, s>>>(upcs, dbias, M, nbp);
         GCL_CHECK_LAUNCH("gcl_linear_bwd_dw_f32(reduce bias)");
       }
       return GCL_OK;

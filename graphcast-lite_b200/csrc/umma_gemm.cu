@@ -975,7 +975,10 @@ template <int NU>
 __global__ void __launch_bounds__(kDwThreads, 1)
     umma_dw_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        float* __restrict__ part, float* __restrict__ part_colsum, int64_t R, int M, int N, int n_pad,
-                       int nst, int nraw, int raw_bytes, int tmem_cols, int64_t rows_per_cta) {
+                       int nst, int nraw, int raw_bytes, int tmem_cols, int64_t rows_per_cta, int wide_b) {
+  // wide_b: B_hi and B_lo are adjacent in a stage, so A_hi x [B_hi | B_lo] is ONE MMA of width 2 n_pad (the A_hi
+  // slab is read from shared memory once instead of twice); its right half and A_lo x B_hi are the correction
+  // terms and get accumulator columns of their own, the epilogue adds the three.
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // the A parts hold only ceil(M / 8) * 8 rows: the M = 128 MMA also reads the following 128 - that rows of
@@ -1009,11 +1012,6 @@ __global__ void __launch_bounds__(kDwThreads, 1)
   if (warp == kEpiWarps) tmem_alloc(smem_u32(tmem_slot), (uint32_t)tmem_cols);
   for (int i = tid; i < nst * stage_bytes / 16; i += kDwThreads)
     reinterpret_cast<float4*>(st_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-  for (int i = tid; i < nst * 8; i += kDwThreads) {
-    uint8_t* b_hi = st_base + (size_t)(i >> 3) * stage_bytes + 2 * a_part;
-    *reinterpret_cast<float4*>(b_hi + sw_off(N, i & 7)) = make_float4(1.f, 1.f, 1.f, 1.f);
-  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -1055,6 +1053,11 @@ __global__ void __launch_bounds__(kDwThreads, 1)
       dst_off[i] = (uint32_t)(isa ? 0 : 2 * a_part) + sw_off(col, chunk);
       lo_off[i] = isa ? (uint32_t)a_part : (uint32_t)b_part;
     }
+    // bias gradient = column sums of A: every A unit keeps the sum of the values it converts (its column, its 4 of
+    // every 32 rows, its K blocks); the partials land in part_colsum[cta][chunk][group][M] and meet in the reduce
+    float cs[NU];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) cs[i] = 0.f;
     const uint32_t st_u32 = smem_u32(st_base), raw_u32 = smem_u32(raw);
     int st = grp % nst, rs = grp % nraw;                  // kDwGroups <= nst, nraw (host guarantees)
     uint32_t ph = 1, rph = 0;
@@ -1070,6 +1073,7 @@ __global__ void __launch_bounds__(kDwThreads, 1)
         if (src_off[i] != 0xffffffffu) {
           const uint32_t a = rbase + src_off[i];
           v[i] = make_float4(lds_f32(a), lds_f32(a + pitch[i]), lds_f32(a + 2 * pitch[i]), lds_f32(a + 3 * pitch[i]));
+          cs[i] += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
       }
 #pragma unroll
@@ -1096,6 +1100,15 @@ __global__ void __launch_bounds__(kDwThreads, 1)
       rs += kDwGroups;
       if (rs >= nraw) { rs -= nraw; rph ^= 1; }
     }
+    if (part_colsum) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        const int u = wi + i * (kDwConv / kDwGroups);
+        const int col = (u >> 3) * 32 + lane, chunk = u & 7;
+        if (u < na_units && col < M)
+          part_colsum[(((int64_t)blockIdx.x * 8 + chunk) * kDwGroups + grp) * M + col] = cs[i];
+      }
+    }
     if (warp < kEpiWarps) {
       // ---- epilogue: the accumulator is complete once the last MMA has retired
       const int m = warp * 32 + lane;
@@ -1107,22 +1120,26 @@ __global__ void __launch_bounds__(kDwThreads, 1)
         for (int c0 = 0; c0 < n_pad; c0 += 16) {
           float v16[16];
           tmem_ld16(taddr + c0, v16);
+          if (wide_b) {                                  // + (A_hi B_lo) + (A_lo B_hi)
+            float c1[16], c2[16];
+            tmem_ld16x2(taddr + n_pad + c0, taddr + 2 * n_pad + c0, c1, c2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v16[j] += c1[j] + c2[j];
+          }
           if (m < M) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int n = c0 + j;
               if (n < N) prow[n] = v16[j];
-              else if (n == N && part_colsum) part_colsum[(int64_t)blockIdx.x * M + m] = v16[j];
             }
           }
         }
       } else if (m < M) {
         for (int n = 0; n < N; ++n) prow[n] = 0.f;
-        if (part_colsum) part_colsum[(int64_t)blockIdx.x * M + m] = 0.f;
       }
     }
   } else {
-    const uint32_t idesc = make_idesc(n_pad, 0, 0);
+    const uint32_t idesc = make_idesc(n_pad, 0, 0), idesc_wide = make_idesc(2 * n_pad, 0, 0);
     const uint32_t st_lo = desc_lo(smem_u32(st_base));
     int st = 0;
     uint32_t ph = 0;
@@ -1133,9 +1150,18 @@ __global__ void __launch_bounds__(kDwThreads, 1)
         const uint32_t ah = st_lo + (uint32_t)st * ((uint32_t)stage_bytes >> 4), al = ah + ((uint32_t)a_part >> 4);
         const uint32_t bh = al + ((uint32_t)a_part >> 4), bl = bh + ((uint32_t)b_part >> 4);
 #ifndef GCL_DW_SKIP_MMA
+        if (wide_b) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_3x(tmem_base, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t acc = (kb | ks) ? 1u : 0u;
+            umma_tf32(tmem_base + 2 * n_pad, desc_k128(al + 2 * ks), desc_k128(bh + 2 * ks), idesc, acc);
+            umma_tf32(tmem_base, desc_k128(ah + 2 * ks), desc_k128(bh + 2 * ks), idesc_wide, acc);
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_3x(tmem_base, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+        }
 #else
         if (kb == 0) umma_3x(tmem_base, ah, al, bh, bl, idesc, 0u);
 #endif
@@ -1374,13 +1400,15 @@ int umma_dw_splits(int64_t R, int64_t M, int64_t N) {
 
 // part[s][M][N], part_colsum[s][M] (nullable) for s < umma_dw_splits(); A [R,M], B [R,N]
 int umma_dw(const float* A, const float* B, float* part, float* part_colsum, int64_t R, int64_t M, int64_t N,
-            cudaStream_t s) {
+            cudaStream_t s, int* n_bias_parts) {
   DwUmmaPlan p = plan_dw(R, M, N);
   if (!p.ok) return GCL_ERR_UNSUPPORTED;
+  if (n_bias_parts) *n_bias_parts = p.grid;
   if (!g_force_register_staging && (M & 3) == 0 && (N & 3) == 0 && al16(A) && al16(B) && R <= 0x7fffff00LL) {
     // raw ring + as many K-major stages as fit
     const int raw_bytes = (int)((kKB * (M + N) * 4 + 127) / 128 * 128);
-    const size_t stage = 2 * (size_t)((M + 7) / 8 * 8) * 128 + 2 * (size_t)p.n_pad * 128;
+    const int n_pad = (int)((N + 15) / 16 * 16);           // no ones-row here: the converters sum the columns of A
+    const size_t stage = 2 * (size_t)((M + 7) / 8 * 8) * 128 + 2 * (size_t)n_pad * 128;
     const size_t fixed = 1024 + 512;
     static const int kDwMinRaw = getenv("GCL_DW_MINRAW") ? atoi(getenv("GCL_DW_MINRAW")) : 6;
     int nst = 4, nraw = 0;
@@ -1394,13 +1422,17 @@ int umma_dw(const float* A, const float* B, float* part, float* part_colsum, int
     if (nst >= kDwGroups && nraw >= kDwGroups && nst >= 2 && nraw >= 2 && (size_t)nraw * raw_bytes >= (size_t)kPartBytes && make_map_2d(&tmA, A, R, M, kKB, (int)M, CU_TENSOR_MAP_SWIZZLE_NONE) &&
         make_map_2d(&tmB, B, R, N, kKB, (int)N, CU_TENSOR_MAP_SWIZZLE_NONE)) {
       const size_t smem = fixed + (size_t)nst * stage + (size_t)nraw * raw_bytes;
+      static const bool no_wide = getenv("GCL_DW_NO_WIDE") && getenv("GCL_DW_NO_WIDE")[0] == '1';
+      const int wide_b = (!no_wide && 2 * n_pad <= 256) ? 1 : 0;     // UMMA N <= 256
+      int wide_cols = 32;
+      while (wide_cols < (wide_b ? 3 : 1) * n_pad) wide_cols <<= 1;
       const int per_grp = kDwConv / kDwGroups;
       const int n_units = 8 * (int)((M + 31) / 32 + (N + 31) / 32), nu = (n_units + per_grp - 1) / per_grp;
       auto launch = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail_cuda(e, "umma_dw_tma(smem attr)");
-        kern<<<p.grid, kDwThreads, smem, s>>>(tmA, tmB, part, part_colsum, R, (int)M, (int)N, p.n_pad, nst, nraw,
-                                              raw_bytes, p.tmem_cols, p.rows_per_cta);
+        kern<<<p.grid, kDwThreads, smem, s>>>(tmA, tmB, part, part_colsum, R, (int)M, (int)N, n_pad, nst, nraw,
+                                              raw_bytes, wide_cols, p.rows_per_cta, wide_b);
         return GCL_OK;
       };
       int rc;
@@ -1411,6 +1443,7 @@ int umma_dw(const float* A, const float* B, float* part, float* part_colsum, int
       else rc = launch(umma_dw_tma_kernel<16>);
       if (rc != GCL_OK) return rc;
       GCL_CHECK_LAUNCH("umma_dw_tma");
+      if (n_bias_parts) *n_bias_parts = p.grid * 8 * kDwGroups;
       return GCL_OK;
     }
   }
