@@ -190,9 +190,9 @@ __device__ __forceinline__ void umma_3x_split(uint32_t d_main, uint32_t d_corr, 
 }
 
 // cute::UMMA::InstrDescriptor: D = F32, A = B = TF32, M = 128, N; major bits 0 = K-major, 1 = MN-major
-__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major, int m = kTileM) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // byte offset of 16-byte chunk `c` (0..7) of row `r` inside a [rows x 128 B] swizzled block
@@ -1111,7 +1111,7 @@ __global__ void __launch_bounds__(kDwThreads, 1)
     }
     if (warp < kEpiWarps) {
       // ---- epilogue: the accumulator is complete once the last MMA has retired
-      const int m = warp * 32 + lane;
+      const int m = M <= 64 ? (lane < 16 ? warp * 16 + lane : M) : warp * 32 + lane;   // see the MMA warp below
       float* prow = part + ((int64_t)blockIdx.x * M + m) * N;
       if (nkb > 0) {
         mbar_wait(bar(kAccFull), 0);
@@ -1139,7 +1139,10 @@ __global__ void __launch_bounds__(kDwThreads, 1)
       }
     }
   } else {
-    const uint32_t idesc = make_idesc(n_pad, 0, 0), idesc_wide = make_idesc(2 * n_pad, 0, 0);
+    // M <= 64: the 64-row MMA shape -- half the A operand reads and half the tensor time; its accumulator row m sits
+    // in TMEM lane 32 (m / 16) + m % 16 (16 lanes per sub-partition, cute tmem_frg_1sm "half subpartitions" atom)
+    const int mm = M <= 64 ? 64 : kTileM;
+    const uint32_t idesc = make_idesc(n_pad, 0, 0, mm), idesc_wide = make_idesc(2 * n_pad, 0, 0, mm);
     const uint32_t st_lo = desc_lo(smem_u32(st_base));
     int st = 0;
     uint32_t ph = 0;
