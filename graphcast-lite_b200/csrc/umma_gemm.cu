@@ -178,16 +178,12 @@ __device__ __forceinline__ void umma_3x(uint32_t d_tmem, uint32_t a_hi, uint32_t
   umma_tf32(d_tmem, desc_k128(a_hi), desc_k128(b_hi), idesc, 1u);
 }
 
-// Same products, but the two correction terms go to their own accumulator.  The tensor core adds into its fp32
-// accumulator with truncation (measured: positive operands come out ~5e-7 low after the 24 accumulation steps
-// of a K = 64 row); keeping the ~2^-11-sized corrections out of the main accumulator leaves it 8 steps, and
-// the epilogue adds the two with an ordinary rounded fp32 add.
-__device__ __forceinline__ void umma_3x_split(uint32_t d_main, uint32_t d_corr, uint32_t a_hi, uint32_t a_lo,
-                                              uint32_t b_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
-  umma_tf32(d_corr, desc_k128(a_lo), desc_k128(b_hi), idesc, accumulate);
-  umma_tf32(d_corr, desc_k128(a_hi), desc_k128(b_lo), idesc, 1u);
-  umma_tf32(d_main, desc_k128(a_hi), desc_k128(b_hi), idesc, accumulate);
-}
+// Accumulator split used by the TMA kernels: the two correction products go to their own accumulator columns.
+// The tensor core adds into its fp32 accumulator with truncation (measured: positive operands come out ~5e-7 low
+// after the 24 accumulation steps of a K = 64 row); keeping the ~2^-11-sized corrections out of the main
+// accumulator leaves it 8 steps, and the epilogue adds the parts with an ordinary rounded fp32 add.  With the hi
+// and lo copies of the N-side operand adjacent in shared memory, A_hi x [B_hi | B_lo] is a single MMA of width
+// 2 n_pad (main | correction columns adjacent in TMEM), followed by A_lo x B_hi into the correction columns.
 
 // cute::UMMA::InstrDescriptor: D = F32, A = B = TF32, M = 128, N; major bits 0 = K-major, 1 = MN-major
 __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major, int m = kTileM) {
@@ -722,9 +718,11 @@ __global__ void __launch_bounds__(kLtThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_block = n_pad * 128;
+  // W per K block: [hi rows | lo rows] adjacent, so that A_hi x [W_hi | W_lo] is one MMA of width 2 n_pad whose
+  // left half lands in the main and whose right half in the correction accumulator (adjacent TMEM columns)
   uint8_t* b_hi = smem;
-  uint8_t* b_lo = b_hi + (size_t)nkb * b_block;
-  uint8_t* raw = b_lo + (size_t)nkb * b_block;
+  uint8_t* b_lo = b_hi + b_block;
+  uint8_t* raw = b_hi + (size_t)nkb * 2 * b_block;
   uint8_t* lo = raw + (size_t)s_raw * kSlabBytes;
   uint8_t* c_out = lo + (size_t)s_lo * kSlabBytes;                     // [nbuf][1 + has_z][nob] slabs
   const int out_buf_bytes = (1 + has_z) * nob * kSlabBytes;
@@ -768,7 +766,7 @@ __global__ void __launch_bounds__(kLtThreads, 1)
     const int k = kb * kKB + c * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < N && k < K) v = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * K + k));
-    split_store(b_hi + (size_t)kb * b_block, b_lo + (size_t)kb * b_block, sw_off(n, c), v);
+    split_store(b_hi + (size_t)kb * 2 * b_block, b_lo + (size_t)kb * 2 * b_block, sw_off(n, c), v);
   }
   for (int n = tid; n < n_pad; n += kLtThreads) bias_s[n] = (bias && n < N) ? __ldg(bias + n) : 0.f;
   for (int n = tid; n < 2 * n_pad; n += kLtThreads) {
@@ -817,10 +815,10 @@ __global__ void __launch_bounds__(kLtThreads, 1)
     }
   } else if (warp == kLtMmaWarp) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    const uint32_t idesc = make_idesc(n_pad, 0, 0);
+    const uint32_t idesc = make_idesc(n_pad, 0, 0), idesc_wide = make_idesc(2 * n_pad, 0, 0);
     const uint32_t raw_lo = desc_lo(smem_u32(raw)), lo_lo = desc_lo(smem_u32(lo));
-    const uint32_t bh_lo = desc_lo(smem_u32(b_hi)), bl_lo = desc_lo(smem_u32(b_lo));
-    const uint32_t b_step = (uint32_t)b_block >> 4;
+    const uint32_t bh_lo = desc_lo(smem_u32(b_hi));
+    const uint32_t b_step = (uint32_t)(2 * b_block) >> 4;
     int rs = 0, ls = 0;
     uint32_t rph = 0, lph = 0;
     int64_t t_local = 0;
@@ -835,12 +833,15 @@ __global__ void __launch_bounds__(kLtThreads, 1)
         tc_fence_after();
         if (elect_one()) {
           const uint32_t ah = raw_lo + (uint32_t)rs * (kSlabBytes >> 4), al = lo_lo + (uint32_t)ls * (kSlabBytes >> 4);
-          const uint32_t bh = bh_lo + (uint32_t)kb * b_step, bl = bl_lo + (uint32_t)kb * b_step;
+          const uint32_t bh = bh_lo + (uint32_t)kb * b_step;
           const int ksteps = min(4, (K - kb * kKB + 7) / 8);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            if (ks < ksteps)
-              umma_3x_split(d_tmem, d_corr, ah + 2 * ks, al + 2 * ks, bh + 2 * ks, bl + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ks < ksteps) {
+              umma_tf32(d_tmem, desc_k128(ah + 2 * ks), desc_k128(bh + 2 * ks), idesc_wide, (kb | ks) ? 1u : 0u);
+              umma_tf32(d_corr, desc_k128(al + 2 * ks), desc_k128(bh + 2 * ks), idesc, 1u);
+            }
+          }
           umma_commit(bar(kRawEmpty + rs));
           umma_commit(bar(kLoEmpty + ls));
           if (kb == nkb - 1) umma_commit(bar(kAccFull + acc));
