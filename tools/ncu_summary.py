@@ -31,7 +31,7 @@ def launches(path):
     print(f"# {len(rows)} launches, {total / 1e3:.1f} us of kernel time in the window (cold-cache, serialised: shares, not absolutes)")
     print("kernel,launches,total_us,avg_us,share")
     for k, (n, ns) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
-        print(f"{k},{n},{ns / 1e3:.1f},{ns / n / 1e3:.2f},{ns / total:.4f}")
+        print(f'"{k}",{n},{ns / 1e3:.1f},{ns / n / 1e3:.2f},{ns / total:.4f}')
 
 
 def full(path):
@@ -60,7 +60,7 @@ def full(path):
                 vals.append(f"{float(v):.4g}")
             except ValueError:
                 vals.append(v)
-        print(short(r[hdr.index("Kernel Name")]) + "," + ",".join(vals))
+        print('"' + short(r[hdr.index("Kernel Name")]) + '",' + ",".join(vals))
 
 
 if __name__ == "__main__":
