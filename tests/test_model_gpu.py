@@ -336,6 +336,31 @@ def test_cuda_graph_capture_of_forward_backward():
     assert l1 > 0 and l2 > 0 and l2 < l1 and int(tr.step_count.item()) == 3
 
 
+def test_device_resident_rollout_and_metrics_match_oracle():
+    """f4: a 3-step autoregressive rollout of the batched model on the GPU (gcl_b200.predict.rollout) against the
+    oracle model driven by the restated reference loop (scripts/predict.py:534-580), and the streaming metrics
+    accumulated on the device against the restated StreamingMetrics."""
+    from gcl_b200 import predict as gp
+    from oracle import predict as op
+    mine, ref, cfg, nlat, nlon = _models("attention", 16, 32, [1, 3], 0.6)
+    G, C, OBS, AR, B = nlat * nlon, 33, 2, 3, 2
+    gen = torch.Generator().manual_seed(11)
+    X, y = torch.randn(B, G, OBS * C, generator=gen), torch.randn(B, G, AR * C, generator=gen)
+    out = gp.rollout(mine, X.to(DEV), AR, C, OBS, y=y.to(DEV), static_ch=(0,), forcing_ch=(5,))
+    assert out.shape == (B, G, AR * C) and out.is_cuda
+    with torch.no_grad():
+        want = torch.stack([op.ar_rollout(lambda inp: ref(X=inp), X[b:b + 1].clone(), AR, C, OBS, y=y[b],
+                                          static_ch=(0,), forcing_ch=(5,)) for b in range(B)])
+    assert_close(out, want, RTOL_F32, "3-step rollout")
+    sm, so = gp.StreamingMetrics(C, (0, 5), device=DEV), op.StreamingMetrics(C, [0, 5])
+    sm.update(y.to(DEV), out)
+    for b in range(B):
+        so.update(y[b], want[b])
+    r = sm.result()
+    assert abs(r["rmse"] - so.rmse) <= 1e-5 * so.rmse and abs(r["acc"] - so.acc) <= 1e-4
+    assert np.allclose(r["rmse_per_channel"], so.rmse_per_channel, rtol=1e-5)
+
+
 def test_import_swap_reference_glue_on_gcl_layers():
     """The reference's model glue (oracle/model.py restates models.py line for line and is pinned
     bit-exact against it) executed with `torch_geometric.nn` resolving to gcl_b200.nn: the drop-in claim
