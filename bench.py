@@ -278,6 +278,21 @@ def run_gcl(args):
             torch.cuda.synchronize(dev)
         infer = {"value": B / (i0.elapsed_time(i1) / n_inf * 1e-3), "unit": "forecast samples/s (forward only, one GPU)",
                  "ms_per_step": i0.elapsed_time(i1) / n_inf}
+        # device-resident 4-step autoregressive rollout + streaming metrics (gcl_b200.predict)
+        from gcl_b200 import predict as gp
+        y4 = torch.randn(B, G, 4 * F, device=dev)
+        sm = gp.StreamingMetrics(F, device=dev)
+        for _ in range(2):
+            sm.update(y4, gp.rollout(model, tr.static_x, 4, F, T))
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(n_inf):
+            sm.update(y4, gp.rollout(model, tr.static_x, 4, F, T))
+        r1.record()
+        torch.cuda.synchronize(dev)
+        infer["rollout4"] = {"value": B / (r0.elapsed_time(r1) / n_inf * 1e-3),
+                             "unit": "4-step forecasts/s incl. streaming RMSE/ACC (one GPU)",
+                             "ms_per_rollout": r0.elapsed_time(r1) / n_inf, "rmse": sm.result()["rmse"]}
 
     # ---- per-kernel CUDA-event timing inside real (eager) steps: roofline of the dominant kernel
     peak, peak_src = measured_peak_gbs()
