@@ -1,0 +1,83 @@
+"""f2 (input pipeline): the product's ChunkedWindowLoader (device-side convert / normalise / transpose; runs on the CPU
+device here) against the oracle restatement and -- where /root/reference is mounted -- against the unmodified
+reference TimeseriesChunkDataset, bit for bit, on synthetic datasets in the reference's on-disk formats."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from gcl_b200.data import ChunkedWindowLoader
+from oracle import data as od
+
+REF = "/root/reference"
+
+
+def _make(tmp, kind, T=14, lon=6, lat=4, F=5, seed=0):
+    rng = np.random.default_rng(seed)
+    np.savez(os.path.join(tmp, "scalers.npz"), mean=rng.normal(size=F).astype(np.float32),
+             std=(0.5 + rng.random(F)).astype(np.float32), n=np.int64(T))
+    if kind == "raw":
+        a = rng.normal(size=(T, lon, lat, F)).astype(np.float16)
+        mm = np.memmap(os.path.join(tmp, "data.npy"), dtype=np.float16, mode="w+", shape=a.shape)
+        mm[:] = a
+        mm.flush()
+        json.dump({"n_time": T, "n_lon": lon, "n_lat": lat, "n_feat": F}, open(os.path.join(tmp, "dataset_info.json"), "w"))
+        return [a]
+    if kind == "flat":
+        a = rng.normal(size=(T, lon * lat, F)).astype(np.float16)
+        mm = np.memmap(os.path.join(tmp, "data.npy"), dtype=np.float16, mode="w+", shape=a.shape)
+        mm[:] = a
+        mm.flush()
+        json.dump({"n_time": T, "n_nodes": lon * lat, "n_feat": F, "flat": True}, open(os.path.join(tmp, "dataset_info.json"), "w"))
+        return [a]
+    parts = [rng.normal(size=(t, lon, lat, F)).astype(np.float16) for t in (T, 3, T - 5)]   # one chunk too short
+    for i, a in enumerate(parts):
+        np.save(os.path.join(tmp, f"chunk_{i}.npy"), a)
+    return parts
+
+
+@pytest.mark.parametrize("kind", ["raw", "flat", "chunks"])
+@pytest.mark.parametrize("split,nf,obs,pred", [("train", None, 2, 1), ("test_only", 3, 2, 4), ("val", None, 4, 4), ("all", 4, 1, 2)])
+def test_loader_matches_oracle_bit_for_bit(tmp_path, kind, split, nf, obs, pred):
+    parts = _make(str(tmp_path), kind)
+    ld = ChunkedWindowLoader(str(tmp_path), obs, pred, split, nf, device="cpu")
+    want_idx = od.sample_indices([p.shape[0] for p in parts], obs, pred, split)
+    assert ld.sample_indices == want_idx and len(ld) == len(want_idx)
+    if not want_idx:
+        return
+    sc = np.load(os.path.join(str(tmp_path), "scalers.npz"))
+    pick = list(range(len(want_idx)))[::2][:5] or [0]
+    X, Y = ld.batch(pick)
+    F = nf or parts[0].shape[-1]
+    assert X.shape == (len(pick), ld.grid_nodes, obs * F) and Y.shape == (len(pick), ld.grid_nodes, pred * F)
+    for b, i in enumerate(pick):
+        ci, t = want_idx[i]
+        x, y = od.window_sample(parts[ci], t, obs, pred, F, sc["mean"].astype(np.float32), sc["std"].astype(np.float32),
+                                kind == "flat")
+        assert np.array_equal(X[b].numpy(), x) and np.array_equal(Y[b].numpy(), y), (kind, split, i)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference not present")
+@pytest.mark.parametrize("kind", ["raw", "flat", "chunks"])
+def test_loader_and_oracle_equal_the_reference_dataset(tmp_path, kind):
+    sys.path.insert(0, REF)
+    try:
+        from src.data.dataloader_chunked import TimeseriesChunkDataset
+    finally:
+        sys.path.remove(REF)
+    parts = _make(str(tmp_path), kind, seed=3)
+    for split, nf, obs, pred in (("train", None, 2, 1), ("test", 3, 2, 3), ("val", None, 3, 2), ("test_only", 4, 2, 4), ("all", None, 2, 2)):
+        ref = TimeseriesChunkDataset(str(tmp_path), obs_window=obs, pred_steps=pred, split=split, n_features=nf)
+        ld = ChunkedWindowLoader(str(tmp_path), obs, pred, split, nf, device="cpu")
+        assert ld.sample_indices == ref._sample_indices
+        assert od.sample_indices([p.shape[0] for p in parts], obs, pred, split) == ref._sample_indices
+        if len(ref) == 0:
+            continue
+        X, Y = ld.batch(range(len(ref)))
+        for i in range(len(ref)):
+            xr, yr = ref[i]
+            assert torch.equal(X[i], xr) and torch.equal(Y[i], yr), (kind, split, i)
