@@ -11,6 +11,7 @@ Results are bit-identical to the reference's (same IEEE float32 operations in th
 import glob
 import json
 import os
+import threading
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -71,14 +72,59 @@ class ChunkedWindowLoader:
             self._stage = t.pin_memory() if self.device.type == "cuda" else t
         return self._stage[:batch]
 
-    def batch(self, indices: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
-        """X [B, G, obs*F], Y [B, G, pred*F] float32 on self.device for the given sample indices."""
-        B, window = len(indices), self.obs_window + self.pred_steps
-        stage = self._staging(B)
+    def _fill(self, stage: torch.Tensor, indices: Sequence[int]):
+        """Host side of a batch: raw float16 window copies memmap -> (pinned) staging, nothing else."""
+        window = self.obs_window + self.pred_steps
         host = stage.numpy()
-        for b, i in enumerate(indices):                                  # raw float16 copies, nothing else on the host
+        for b, i in enumerate(indices):
             ci, t = self.sample_indices[int(i)]
             host[b] = self.chunks[ci][t: t + window]
+
+    def batch(self, indices: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+        """X [B, G, obs*F], Y [B, G, pred*F] float32 on self.device for the given sample indices."""
+        stage = self._staging(len(indices))
+        self._fill(stage, indices)
+        return self._to_device(stage)
+
+    def batches(self, batch_size: int, shuffle: bool = False, seed: int = 0, drop_last: bool = False,
+                rank: int = 0, world: int = 1):
+        """Iterate over the split in batches (rank r of a data-parallel job takes samples r::world).  The host copy of
+        batch k+1 runs on a worker thread into a second staging buffer while batch k is being consumed; a staging
+        buffer is rewritten only after the H2D copy that read it has completed."""
+        order = np.arange(len(self.sample_indices))
+        if shuffle:
+            order = np.random.default_rng(seed).permutation(order)
+        order = order[rank::world]
+        groups = [order[i: i + batch_size] for i in range(0, len(order), batch_size)]
+        if drop_last and groups and len(groups[-1]) < batch_size:
+            groups.pop()
+        if not groups:
+            return
+        window = self.obs_window + self.pred_steps
+        cuda = self.device.type == "cuda"
+        stages, events = [], []
+        for _ in range(2):
+            t = torch.empty((batch_size, window) + self.frame_shape, dtype=torch.float16)
+            stages.append(t.pin_memory() if cuda else t)
+            events.append(torch.cuda.Event() if cuda else None)
+        worker = threading.Thread(target=self._fill, args=(stages[0][: len(groups[0])], groups[0]))
+        worker.start()
+        for k, g in enumerate(groups):
+            worker.join()                                            # staging k % 2 holds batch k
+            cur = k % 2
+            if k + 1 < len(groups):
+                nxt = (k + 1) % 2
+                if cuda and k >= 1:
+                    events[nxt].synchronize()                        # the H2D copy of batch k-1 has left that buffer
+                worker = threading.Thread(target=self._fill, args=(stages[nxt][: len(groups[k + 1])], groups[k + 1]))
+                worker.start()
+            out = self._to_device(stages[cur][: len(g)])
+            if cuda:
+                events[cur].record(torch.cuda.current_stream(self.device))
+            yield out
+
+    def _to_device(self, stage: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        B, window = stage.shape[0], self.obs_window + self.pred_steps
         raw = stage.to(self.device, non_blocking=True)
         w = (raw[..., : self.n_feat].float() - self.mean) / self.std     # dataloader_chunked.py:190-191 / 204-207
         if self.flat_grid:                                               # [B, W, N, F] -> [B, N, W, F]        (:196-199)

@@ -81,3 +81,23 @@ def test_loader_and_oracle_equal_the_reference_dataset(tmp_path, kind):
         for i in range(len(ref)):
             xr, yr = ref[i]
             assert torch.equal(X[i], xr) and torch.equal(Y[i], yr), (kind, split, i)
+
+
+def test_prefetching_iterator_covers_the_split_deterministically(tmp_path):
+    _make(str(tmp_path), "raw", T=23)
+    ld = ChunkedWindowLoader(str(tmp_path), 2, 2, "all", None, device="cpu")
+    n = len(ld)
+    plain = [ld.batch(range(i, min(i + 4, n))) for i in range(0, n, 4)]
+    got = list(ld.batches(4))
+    assert len(got) == len(plain) and all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(got, plain))
+    assert len(list(ld.batches(4, drop_last=True))) == n // 4
+    # shuffled: same permutation for the same seed, every sample exactly once, ranks take disjoint strides
+    a = torch.cat([x for x, _ in ld.batches(3, shuffle=True, seed=7)])
+    b = torch.cat([x for x, _ in ld.batches(3, shuffle=True, seed=7)])
+    assert torch.equal(a, b) and a.shape[0] == n
+    full = torch.cat([x for x, _ in ld.batches(n)])
+    key = lambda t: sorted(map(tuple, t.reshape(t.shape[0], -1)[:, :6].tolist()))
+    assert key(a) == key(full)
+    r0 = torch.cat([x for x, _ in ld.batches(3, rank=0, world=2)])
+    r1 = torch.cat([x for x, _ in ld.batches(3, rank=1, world=2)])
+    assert r0.shape[0] + r1.shape[0] == n and key(torch.cat([r0, r1])) == key(full)

@@ -31,3 +31,16 @@ def test_loader_on_device_is_bit_exact(tmp_path, kind):
         assert np.array_equal(X[b].cpu().numpy(), x) and np.array_equal(Y[b].cpu().numpy(), y), (kind, i)
     X2, _ = ld.batch(pick[:2])                      # staging buffer reuse with a smaller batch
     assert torch.equal(X2, X[:2])
+
+
+def test_prefetching_iterator_on_device(tmp_path):
+    """batches(): worker-thread staging + event-guarded buffer reuse gives the same tensors as batch()."""
+    from gcl_b200.data import ChunkedWindowLoader
+    _make(str(tmp_path), "raw", T=40, lon=16, lat=8, F=7, seed=9)
+    ld = ChunkedWindowLoader(str(tmp_path), 2, 1, "all", None, device="cuda:0")
+    n = len(ld)
+    got = [(x.clone(), y.clone()) for x, y in ld.batches(5)]
+    assert sum(x.shape[0] for x, _ in got) == n
+    for k, (x, y) in enumerate(got):
+        xr, yr = ld.batch(range(5 * k, min(5 * k + 5, n)))
+        assert torch.equal(x, xr) and torch.equal(y, yr), k
