@@ -38,6 +38,13 @@ class ChunkedWindowLoader:
                 raise FileNotFoundError(f"No data.npy or chunk_*.npy found in {data_dir}")
             self.chunks = [np.load(f, mmap_mode="r") for f in files]
         c0 = self.chunks[0]
+        # legacy chunk files keep whatever dtype they were saved with (the reference converts with
+        # .astype(np.float32), :190); the staging buffers take the stored dtype and the device converts
+        self.raw_dtype = torch.from_numpy(np.empty(0, dtype=c0.dtype)).dtype
+        if any(ch.dtype != c0.dtype for ch in self.chunks):
+            raise ValueError("gcl_b200.data: all chunk files must share one dtype")
+        if not self.raw_dtype.is_floating_point:
+            raise ValueError(f"gcl_b200.data: unsupported chunk dtype {c0.dtype}")
         self.n_feat_total = c0.shape[-1]
         self.n_feat = int(n_features) if n_features else self.n_feat_total
         self.frame_shape = tuple(c0.shape[1:])                          # (lon, lat, F_total) or (N, F_total)
@@ -61,6 +68,7 @@ class ChunkedWindowLoader:
             raise ValueError(f"Unknown split: {split}")
         self.sample_indices = idx
         self._stage = None
+        self._stage_free = None          # event: the H2D copy that last read self._stage has completed
 
     def __len__(self):
         return len(self.sample_indices)
@@ -68,7 +76,7 @@ class ChunkedWindowLoader:
     def _staging(self, batch: int) -> torch.Tensor:
         window = self.obs_window + self.pred_steps
         if self._stage is None or self._stage.shape[0] < batch:
-            t = torch.empty((batch, window) + self.frame_shape, dtype=torch.float16)
+            t = torch.empty((batch, window) + self.frame_shape, dtype=self.raw_dtype)
             self._stage = t.pin_memory() if self.device.type == "cuda" else t
         return self._stage[:batch]
 
@@ -82,18 +90,28 @@ class ChunkedWindowLoader:
 
     def batch(self, indices: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
         """X [B, G, obs*F], Y [B, G, pred*F] float32 on self.device for the given sample indices."""
+        if self._stage_free is not None:
+            self._stage_free.synchronize()       # the previous batch()'s H2D copy may still be reading the buffer
         stage = self._staging(len(indices))
         self._fill(stage, indices)
-        return self._to_device(stage)
+        out = self._to_device(stage)
+        if self.device.type == "cuda":
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream(self.device))
+        return out
 
     def batches(self, batch_size: int, shuffle: bool = False, seed: int = 0, drop_last: bool = False,
                 rank: int = 0, world: int = 1):
-        """Iterate over the split in batches (rank r of a data-parallel job takes samples r::world).  The host copy of
-        batch k+1 runs on a worker thread into a second staging buffer while batch k is being consumed; a staging
-        buffer is rewritten only after the H2D copy that read it has completed."""
+        """Iterate over the split in batches (rank r of a data-parallel job takes samples r::world).  Every rank gets
+        the same number of samples -- the order is wrap-padded to a multiple of `world` first, as
+        torch.utils.data.DistributedSampler does -- so all ranks run the same number of (collective) steps.  The host
+        copy of batch k+1 runs on a worker thread into a second staging buffer while batch k is being consumed; a
+        staging buffer is rewritten only after the H2D copy that read it has completed."""
         order = np.arange(len(self.sample_indices))
         if shuffle:
             order = np.random.default_rng(seed).permutation(order)
+        if world > 1 and len(order) % world:
+            order = np.concatenate([order, order[: world - len(order) % world]])
         order = order[rank::world]
         groups = [order[i: i + batch_size] for i in range(0, len(order), batch_size)]
         if drop_last and groups and len(groups[-1]) < batch_size:
@@ -104,7 +122,7 @@ class ChunkedWindowLoader:
         cuda = self.device.type == "cuda"
         stages, events = [], []
         for _ in range(2):
-            t = torch.empty((batch_size, window) + self.frame_shape, dtype=torch.float16)
+            t = torch.empty((batch_size, window) + self.frame_shape, dtype=self.raw_dtype)
             stages.append(t.pin_memory() if cuda else t)
             events.append(torch.cuda.Event() if cuda else None)
         worker = threading.Thread(target=self._fill, args=(stages[0][: len(groups[0])], groups[0]))

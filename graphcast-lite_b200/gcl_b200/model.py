@@ -79,6 +79,7 @@ class SparseGATConv(GATConv):
 
     def __init__(self, in_channels, out_channels, heads=1, concat=False, dropout=0.0, bias=True, **kw):
         super().__init__(in_channels, out_channels, heads, concat=concat, dropout=dropout, bias=bias, **kw)
+        self.process_group = None        # set by Trainer(process_group=...): the replicas that prune together
 
     def forward(self, x, edge_index, attention_threshold=0.0, **kwargs):
         batch_num = kwargs.get("batch_num", 1)
@@ -87,12 +88,12 @@ class SparseGATConv(GATConv):
             att = att.mean(dim=0)
         att = att.squeeze()
         if batch_num == 0:
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
                 # data-parallel replicas must keep the SAME edge set: prune on the attention averaged over the
-                # global batch (the reference is single-process, models.py:140-149)
+                # global batch of the trainer's process group (the reference is single-process, models.py:140-149)
                 att = att.contiguous()
-                dist.all_reduce(att, op=dist.ReduceOp.SUM)
-                att = att / dist.get_world_size()
+                dist.all_reduce(att, op=dist.ReduceOp.SUM, group=self.process_group)
+                att = att / dist.get_world_size(self.process_group)
             edge_index = ops.edge_prune(edge_index, att, float(attention_threshold))
         return out, (edge_index, att)
 

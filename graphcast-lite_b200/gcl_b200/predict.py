@@ -55,6 +55,7 @@ class StreamingMetrics:
             keep[int(c)] = False
         f64 = dict(dtype=torch.float64, device=device)
         self.keep = keep.to(device)
+        self.n_keep = int(keep.sum())               # host-side count: update() must not synchronise
         self.n = 0
         self.sum_se, self.sum_ae = torch.zeros((), **f64), torch.zeros((), **f64)
         self.total_elem = 0
@@ -83,7 +84,7 @@ class StreamingMetrics:
         keep_cols = self.keep.repeat(P)
         self.sum_se += se.double()[:, keep_cols].sum()
         self.sum_ae += ae.double()[:, keep_cols].sum()
-        self.total_elem += B * G * int(keep_cols.sum())
+        self.total_elem += B * G * P * self.n_keep
         self.n += B
 
     def result(self) -> dict:

@@ -74,6 +74,9 @@ class Trainer:
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.ar_steps, self.use_residual = int(ar_steps), use_residual
         self.pg = process_group
+        for m in model.modules():            # SparseGATConv prunes on the attention averaged over THIS group
+            if hasattr(m, "process_group"):
+                m.process_group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         params, seen = [], set()
         for p in model.parameters():

@@ -101,3 +101,42 @@ def test_prefetching_iterator_covers_the_split_deterministically(tmp_path):
     r0 = torch.cat([x for x, _ in ld.batches(3, rank=0, world=2)])
     r1 = torch.cat([x for x, _ in ld.batches(3, rank=1, world=2)])
     assert r0.shape[0] + r1.shape[0] == n and key(torch.cat([r0, r1])) == key(full)
+
+
+def test_rank_shards_are_equal_when_the_split_does_not_divide(tmp_path):
+    """n % world != 0: every rank must see the same number of batches of the same shapes (each step ends in a
+    collective), the order being wrap-padded like DistributedSampler's; every sample is still covered."""
+    _make(str(tmp_path), "raw", T=23)
+    ld = ChunkedWindowLoader(str(tmp_path), 2, 2, "all", None, device="cpu")
+    n = len(ld)
+    for world, bs in ((3, 2), (3, 1), (6, 3), (7, 2)):
+        assert n % world != 0
+        per_rank = [list(ld.batches(bs, shuffle=True, seed=3, rank=r, world=world)) for r in range(world)]
+        shapes = [[tuple(x.shape) for x, _ in b] for b in per_rank]
+        assert all(s == shapes[0] for s in shapes), (world, bs, shapes)
+        key = lambda t: set(map(tuple, t.reshape(t.shape[0], -1)[:, :6].tolist()))
+        full = torch.cat([x for x, _ in ld.batches(n)])
+        seen = set().union(*[key(torch.cat([x for x, _ in b])) for b in per_rank])
+        assert seen == key(full)
+        per_rank_d = [list(ld.batches(bs, rank=r, world=world, drop_last=True)) for r in range(world)]
+        assert len({len(b) for b in per_rank_d}) == 1
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_legacy_chunks_of_other_float_dtypes_are_not_quantised(tmp_path, dtype):
+    """chunk_*.npy keep their stored dtype; the reference does .astype(np.float32) (dataloader_chunked.py:190)."""
+    rng = np.random.default_rng(5)
+    T, lon, lat, F = 9, 5, 3, 4
+    np.savez(os.path.join(tmp_path, "scalers.npz"), mean=rng.normal(size=F).astype(np.float32),
+             std=(0.5 + rng.random(F)).astype(np.float32), n=np.int64(T))
+    a = (rng.normal(size=(T, lon, lat, F)) * 1e5).astype(dtype)          # beyond float16's range
+    np.save(os.path.join(tmp_path, "chunk_0.npy"), a)
+    ld = ChunkedWindowLoader(str(tmp_path), 2, 1, "all", None, device="cpu")
+    X, Y = ld.batch([0, 3])
+    sc = np.load(os.path.join(tmp_path, "scalers.npz"))
+    for b, t in enumerate((0, 3)):
+        w = (a[t:t + 3].astype(np.float32) - sc["mean"]) / sc["std"]
+        w = w.transpose(2, 1, 0, 3).reshape(lon * lat, 3, F)
+        assert np.array_equal(X[b].numpy(), w[:, :2].reshape(lon * lat, 2 * F))
+        assert np.array_equal(Y[b].numpy(), w[:, 2:].reshape(lon * lat, F))
+        assert np.isfinite(X[b].numpy()).all()
