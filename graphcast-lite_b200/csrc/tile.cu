@@ -1,0 +1,777 @@
+// Tiled segmented SpMM / single-head GAT aggregation (K2/K3/K4/K6, second generation).
+//
+// Same arithmetic as spmm.cu / gat.cu (out[b,i,:] = epi(sum_k w[k] x[b,col[k],:]), entries of a row in ascending
+// CSR order, no atomics), but a CTA owns a *tile* of rows and the union of their source rows is staged in shared
+// memory by asynchronous bulk copies (tile.cuh).  Replaces PyG's propagate (index_select -> mul -> scatter_add_)
+// at /root/reference/src/models.py:414 (SimpleConv), :419 (GCNConv) and, with MODE 2, the whole message passing of
+// a single-head GATConv (:425): logits, LeakyReLU, segment softmax and aggregation in one kernel.
+//
+//   gcl_tile_plan_host   host-side greedy tiling of a CSR (once per graph / orientation, cached by the caller)
+//   gcl_spmm_tiled_f32   GCN / mean / unit weights (+ bias, PReLU, pre-activation copy): persistent, warp-specialised
+//                        CTAs walk the (tile, sample block) items through a 3-stage shared-memory ring
+//                        (spmm_ws_kernel: a producer warp issues the copies, 16 consumer warps reduce); heavy
+//                        rows (more entries than a tile's union may hold, e.g. the 687-entry polar rows of the
+//                        512x256 grid->mesh graph) by a CTA-per-row kernel with a fixed-order two-phase reduction
+//   gcl_gat_fwd_tiled_f32  heads == 1 GATConv forward: alpha computed inside the tile CTA
+#include <algorithm>
+#include <vector>
+
+#include "tile.cuh"
+
+namespace gcl {
+namespace {
+
+__device__ __forceinline__ float leaky_f(float v, float slope) { return v > 0.f ? v : slope * v; }
+
+// shared-memory carve-up (bytes) for a plan / channel count / SB / number of per-entry weight planes
+struct TileSmem {
+  size_t xs, ew, re, rid, as, eli, total;
+};
+inline TileSmem tile_smem(const TileArgs& p, int C, int SB, int wplanes, bool scores) {
+  TileSmem s;
+  size_t o = 128;                                         // mbarrier + padding
+  s.xs = o;  o += (size_t)SB * p.max_union * C * 4;
+  s.ew = o;  o += (size_t)wplanes * p.max_entries * 4;
+  s.re = o;  o += ((size_t)p.max_rows + 1) * 4;
+  s.rid = o; o += (size_t)p.max_rows * 4;
+  s.as = o;  o += scores ? (size_t)SB * p.max_union * 4 : 0;
+  s.eli = o; o += (size_t)p.max_entries * 2;
+  s.total = (o + 15) & ~size_t(15);
+  return s;
+}
+
+// MODE 0: one weight per CSR entry shared by all samples (w nullable = 1)           -- GCNConv / SimpleConv
+// MODE 1: per-sample weights w[b][k] (w_bstride apart) times w_scale                 -- aggregation with given alpha
+// MODE 2: weights = segment softmax of LeakyReLU(a_src[col] + a_dst[row]), written to alpha_csr (/ alpha_pyg)
+template <int L, int SB, int MODE>
+__global__ void __launch_bounds__(kTileThreads)
+    spmm_tile_kernel(TileArgs p, TileSmem sm, const float* __restrict__ w, const float* __restrict__ x,
+                     float* __restrict__ out, int C, int64_t x_bstride, int64_t out_bstride, int B,
+                     const float* __restrict__ bias, const float* __restrict__ prelu_slope, float* __restrict__ z_out,
+                     int64_t w_bstride, float w_scale, const float* __restrict__ a_src, const float* __restrict__ a_dst,
+                     int64_t a_bstride, float neg_slope, float* __restrict__ alpha_csr, float* __restrict__ alpha_pyg,
+                     const int32_t* __restrict__ perm, int64_t nnz) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int WP = MODE == 0 ? 1 : SB;
+  float* xs = reinterpret_cast<float*>(smem + sm.xs);
+  float* e_w = reinterpret_cast<float*>(smem + sm.ew);
+  int32_t* r_e = reinterpret_cast<int32_t*>(smem + sm.re);
+  int32_t* r_id = reinterpret_cast<int32_t*>(smem + sm.rid);
+  float* as_s = reinterpret_cast<float*>(smem + sm.as);
+  uint16_t* e_li = reinterpret_cast<uint16_t*>(smem + sm.eli);
+  const uint32_t bar = tile_smem_u32(smem);
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.y * SB;
+  const int nb = min(SB, B - b0);
+  const TileHdr h = tile_header(p, blockIdx.x);
+
+  if (tid == 0) tile_mbar_init(bar, 1);
+  __syncthreads();
+  tile_issue_rows(p, h, x, x_bstride, C, b0, nb, xs, bar);
+
+  // tile metadata -> shared memory while the rows are in flight
+  for (int i = tid; i <= h.nr; i += kTileThreads) {
+    r_e[i] = __ldg(p.eptr + h.r0 + i) - h.e0;
+    if (i < h.nr) r_id[i] = __ldg(p.rows + h.r0 + i);
+  }
+  for (int le = tid; le < h.ne; le += kTileThreads) {
+    e_li[le] = p.lidx[h.e0 + le];
+    if (MODE != 2) {
+      const int32_t k = __ldg(p.ek + h.e0 + le);
+      if (MODE == 0) {
+        e_w[le] = w ? __ldg(w + k) : 1.f;
+      } else {
+#pragma unroll
+        for (int s = 0; s < SB; ++s)
+          if (s < nb) e_w[s * p.max_entries + le] = w[(int64_t)(b0 + s) * w_bstride + k] * w_scale;
+      }
+    }
+  }
+  if (MODE == 2) {
+    for (int idx = tid; idx < h.nu * nb; idx += kTileThreads) {
+      const int s = idx / h.nu, u = idx - s * h.nu;
+      as_s[s * p.max_union + u] = __ldg(a_src + (int64_t)(b0 + s) * a_bstride + __ldg(p.usrc + h.u0 + u));
+    }
+  }
+  __syncthreads();
+  if (MODE == 2) {
+    // attention coefficients: one thread per (row, sample); PyG softmax: exp(e - max) / (sum + 1e-16)
+    for (int item = tid; item < h.nr * nb; item += kTileThreads) {
+      const int s = item / h.nr, i = item - s * h.nr;
+      const float adi = __ldg(a_dst + (int64_t)(b0 + s) * a_bstride + r_id[i]);
+      const float* asb = as_s + s * p.max_union;
+      float* ew = e_w + s * p.max_entries;
+      const int le0 = r_e[i], le1 = r_e[i + 1];
+      float m = -INFINITY;
+      for (int le = le0; le < le1; ++le) {
+        const float e = leaky_f(asb[e_li[le]] + adi, neg_slope);
+        ew[le] = e;
+        m = fmaxf(m, e);
+      }
+      float l = 0.f;
+      for (int le = le0; le < le1; ++le) {
+        const float pe = __expf(ew[le] - m);
+        ew[le] = pe;
+        l += pe;
+      }
+      const float rl = 1.f / (l + 1e-16f);
+      float* ac = alpha_csr + (int64_t)(b0 + s) * nnz;
+      float* ap = alpha_pyg ? alpha_pyg + (int64_t)(b0 + s) * nnz : nullptr;
+      for (int le = le0; le < le1; ++le) {
+        const float al = ew[le] * rl;
+        ew[le] = al;
+        const int32_t k = __ldg(p.ek + h.e0 + le);
+        ac[k] = al;
+        if (ap) ap[__ldg(perm + k)] = al;
+      }
+    }
+    __syncthreads();
+  }
+  tile_mbar_wait(bar, 0);
+
+  // aggregation: a group of L lanes (one 128-bit word each) per row, rows of the tile round-robin over the groups
+  constexpr int kGroups = kTileThreads / L;
+  const int gl = tid & (L - 1), grp = tid / L;
+  const int off = gl * 4;
+  const bool live = off < C;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias && live) bv = ldg4(bias + off);
+  const float slope = prelu_slope ? __ldg(prelu_slope) : 0.f;
+  const int xs_sstride = p.max_union * C;
+  for (int i = grp; i < h.nr; i += kGroups) {
+    if (!live) continue;
+    const int le0 = r_e[i], le1 = r_e[i + 1];
+    float4 acc[SB];
+#pragma unroll
+    for (int s = 0; s < SB; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int le = le0; le < le1; ++le) {
+      const uint32_t li = e_li[le];
+      if (li != kMasked) {
+        const float* xr = xs + li * C + off;
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+          if (s < nb) {
+            const float4 v = *reinterpret_cast<const float4*>(xr + s * xs_sstride);
+            fma4(acc[s], e_w[(WP == 1 ? 0 : s * p.max_entries) + le], v);
+          }
+        }
+      }
+    }
+    const int64_t row = r_id[i];
+#pragma unroll
+    for (int s = 0; s < SB; ++s) {
+      if (s >= nb) break;
+      float4 a = make_float4(acc[s].x + bv.x, acc[s].y + bv.y, acc[s].z + bv.z, acc[s].w + bv.w);
+      const int64_t o = (int64_t)(b0 + s) * out_bstride + row * C + off;
+      if (z_out) st4(z_out + o, a);
+      if (prelu_slope) a = make_float4(prelu_f(a.x, slope), prelu_f(a.y, slope), prelu_f(a.z, slope), prelu_f(a.w, slope));
+      st4(out + o, a);
+    }
+  }
+}
+
+// ---- persistent, warp-specialised SpMM ----------------------------------------------------------------------
+// One CTA per SM walks items (sample block, tile) = blockIdx.x, + gridDim.x, ...  through a ring of kWsStages
+// shared-memory stages.  Stage = the union's rows of SB samples (+ one all-zero row that pad / masked entries
+// point to), the tile's packed entries {lidx, weight}, its row ids, entry offsets and descriptor.
+//   warps 0..3 (producers): wait for the stage to be released (mbarrier `empty`), issue the item's copies -- 16-byte
+//     cp.async chunks for the rows (source-row ids come from a small shared-memory buffer filled one item ahead),
+//     4/8/16-byte cp.async for the index data -- and lets the copies themselves signal `full`
+//     (cp.async.mbarrier.arrive.noinc): the producers never wait for data and run up to kWsStages items ahead.
+//   warps 4..19 (consumers): wait for `full`, reduce the tile's rows out of shared memory, release the stage.
+// The first tiled version (load -> sync -> compute inside one short-lived CTA) and a version in which all warps
+// both copied and computed were bound by the per-item latency chain (header -> source ids -> rows -> barrier), not
+// by HBM or by the gathers (ncu: barrier + scoreboard stalls, < 30% of DRAM peak).
+// The reduction is written for instruction count (ncu: 67 M warp instructions for 10 M FFMAs before): a lane owns
+// TWO 128-bit words of a row (a group of L = words/2 lanes per row), entries come as pairs from one LDS.128, pad
+// entries point at the zero row (no bounds test in the loop), and the products use the packed FFMA2
+// (fma.rn.f32x2, bit-identical to two fmaf).
+#ifndef GCL_WS_STAGES
+#define GCL_WS_STAGES 3
+#endif
+#ifndef GCL_WS_CW
+#define GCL_WS_CW 16
+#endif
+#ifndef GCL_WS_PW
+#define GCL_WS_PW 12
+#endif
+constexpr int kWsStages = GCL_WS_STAGES;
+constexpr int kWsConsumerWarps = GCL_WS_CW;
+constexpr int kWsProducerWarps = GCL_WS_PW;
+constexpr int kWsThreads = 32 * (kWsConsumerWarps + kWsProducerWarps);
+
+struct WsSmem {
+  int xs, ent, re, rid, desc, stage, us, bars, total;     // byte offsets (inside a stage / the CTA) and sizes
+};
+inline WsSmem ws_smem(const TileArgs& p, int C, int SB) {
+  WsSmem s;
+  int o = 0;
+  s.xs = o;   o += SB * (p.max_union + 1) * C * 4;
+  s.ent = o;  o += ((p.max_entries + 1) & ~1) * 8;
+  s.re = o;   o += ((p.max_rows + 1 + 3) & ~3) * 4;
+  s.rid = o;  o += ((p.max_rows + 3) & ~3) * 4;
+  s.desc = o; o += 32;
+  s.stage = (o + 127) & ~127;
+  s.us = kWsStages * s.stage;                              // source-row ids of the next two items
+  s.bars = s.us + 2 * ((p.max_union + 3) & ~3) * 4;
+  s.total = s.bars + 16 * kWsStages;
+  return s;
+}
+
+// acc.{x,y} += w * v.{x,y}; acc.{z,w} += w * v.{z,w}   (two FFMA2)
+__device__ __forceinline__ void fma4_packed(float4& acc, float w, const float4& v) {
+  unsigned long long a0, a1, v0, v1, ww;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w), "f"(w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(acc.x), "f"(acc.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(acc.z), "f"(acc.w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v0) : "f"(v.x), "f"(v.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v1) : "f"(v.z), "f"(v.w));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(v0), "l"(ww));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(v1), "l"(ww));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a0));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.z), "=f"(acc.w) : "l"(a1));
+}
+__device__ __forceinline__ void ws_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ws_cp4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src) : "memory");
+}
+// the executing thread arrives on `bar` once all its earlier cp.async copies have landed (the arrival is part of
+// the barrier's expected count: .noinc)
+__device__ __forceinline__ void ws_cp_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+// consumer-side wait: back off between polls so that the spinning warps do not take issue slots from the producers
+__device__ __forceinline__ void ws_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  while (!done) {
+#ifdef GCL_WS_SLEEP
+    __nanosleep(GCL_WS_SLEEP);
+#endif
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void ws_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+
+// LC = lanes that cover a row in 16-byte chunks (copy mapping); the reduction uses L = LC/2 lanes per row, each
+// owning words gl and gl + L (LC = 4: one word per lane)
+template <int LC, int SB>
+__global__ void __launch_bounds__(kWsThreads, 1)
+    spmm_ws_kernel(TileArgs p, WsSmem sm, const int2* __restrict__ ent, const float* __restrict__ x,
+                   float* __restrict__ out, int C, int64_t x_bstride, int64_t out_bstride, int B, int n_items,
+                   const float* __restrict__ bias, const float* __restrict__ prelu_slope, float* __restrict__ z_out,
+                   int dbg) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int words = C >> 2;
+  const int T = p.n_tiles;
+  const int zrow = p.max_union;                    // index of the all-zero row of a stage
+  const int n_my = blockIdx.x < n_items ? (n_items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const uint32_t rowb = (uint32_t)C * 4u;
+  const uint32_t sstride = (uint32_t)(zrow + 1) * rowb;
+  const uint32_t smem_base = tile_smem_u32(smem);
+  const uint32_t full0 = smem_base + sm.bars, empty0 = full0 + 8 * kWsStages;
+
+  for (int idx = tid; idx < kWsStages * SB * words; idx += kWsThreads) {      // the all-zero rows
+    const int st = idx / (SB * words), r = idx - st * SB * words, s = r / words, wd = r - s * words;
+    *reinterpret_cast<float4*>(smem + st * sm.stage + sm.xs + (uint32_t)s * sstride + (uint32_t)zrow * rowb + wd * 16) =
+        make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (tid == 0) {
+    for (int st = 0; st < kWsStages; ++st) {
+      tile_mbar_init(full0 + 8 * st, 32 * kWsProducerWarps); // every producer lane's copies arrive
+      tile_mbar_init(empty0 + 8 * st, kWsConsumerWarps);     // one arrival per consumer warp
+    }
+  }
+  __syncthreads();
+
+  if (warp < kWsProducerWarps) {
+    // ------------------------------------------------------------------------------------------- producers
+    // kWsProducerWarps warps share an item: copy group g = ptid / LC takes rows g, g + NG, ...; a warp requests
+    // exactly the source ids its own groups will use, so its private cp.async groups + __syncwarp order them.
+    constexpr int NG = 32 * kWsProducerWarps / LC;           // rows per pass of all producer threads
+    constexpr int RW = 32 / LC;                              // rows per warp-wide copy instruction
+    const int ptid = tid;                                    // producers are warps 0 .. kWsProducerWarps-1
+    const int part = lane & (LC - 1), g = ptid / LC;
+    const bool clive = part < words;
+    const int usz = ((zrow + 3) & ~3) * 4;                   // bytes of one source-id buffer
+    auto load_desc = [&](int j, int4& a, int4& b) {
+      if (j < n_my) {
+        const int4* dp = reinterpret_cast<const int4*>(p.tile_desc) + 2 * ((blockIdx.x + j * (int)gridDim.x) % T);
+        a = __ldg(dp);                                       // {r0, nr, u0, nu}
+        b = __ldg(dp + 1);                                   // {e0, ne, 0, 0}
+      } else {
+        a = b = make_int4(0, 0, 0, 0);
+      }
+    };
+    auto request_usrc = [&](int j, const int4& a) {          // this warp's source-row ids of item j -> us[j & 1]
+      for (int q = lane; ; q += 32) {
+        const int u = (q / RW) * NG + warp * RW + (q % RW);
+        if (u >= a.w) break;
+        ws_cp4(smem_base + sm.us + (j & 1) * usz + 4 * u, p.usrc + a.z + u);
+      }
+      cp_async_commit();
+    };
+    int4 da, db, na, nbq, fa, fb;                            // descriptors of items j, j+1, j+2
+    load_desc(0, da, db);
+    load_desc(1, na, nbq);
+    request_usrc(0, da);
+    for (int j = 0; j < n_my; ++j) {
+      const int slot = j % kWsStages;
+      request_usrc(j + 1, na);                               // commit order: ids(j+1) before rows(j)
+      load_desc(j + 2, fa, fb);                              // lands while this item's copies are issued
+      const int item = blockIdx.x + j * gridDim.x;
+      const int b0 = (item / T) * SB;
+      const int nb = min(SB, B - b0);
+      tile_mbar_wait(empty0 + 8 * slot, (uint32_t)(((j / kWsStages) & 1) ^ 1));   // consumers released the stage
+      if (j == 0) cp_async_wait<1>();              // ids(j) landed (ids(j+1) and rows(j-1) may still be in flight)
+      else cp_async_wait<2>();
+      __syncwarp();
+      const uint32_t st = smem_base + (uint32_t)slot * (uint32_t)sm.stage;
+      const int32_t* us = reinterpret_cast<const int32_t*>(smem + sm.us + (j & 1) * usz);
+      if (clive && !(dbg & 1)) {
+        // per-sample source pointers once per item; a row then costs one 32-bit multiply and, per sample, one
+        // 64-bit add and the copy (n_nodes * C < 2^31 is checked by the host)
+        const float* xp[SB];
+#pragma unroll
+        for (int s = 0; s < SB; ++s) xp[s] = x + (int64_t)(b0 + min(s, nb - 1)) * x_bstride + part * 4;
+        const uint32_t dst0 = st + sm.xs + part * 16;
+        if (nb == SB) {
+#pragma unroll 4
+          for (int u = g; u < da.w; u += NG) {
+            const uint32_t off = (uint32_t)us[u] * (uint32_t)C;
+            const uint32_t dst = dst0 + (uint32_t)u * rowb;
+#pragma unroll
+            for (int s = 0; s < SB; ++s) ws_cp16(dst + s * sstride, xp[s] + off);
+          }
+        } else {
+          for (int u = g; u < da.w; u += NG) {
+            const uint32_t off = (uint32_t)us[u] * (uint32_t)C;
+            const uint32_t dst = dst0 + (uint32_t)u * rowb;
+#pragma unroll
+            for (int s = 0; s < SB; ++s)
+              if (s < nb) ws_cp16(dst + s * sstride, xp[s] + off);
+          }
+        }
+      }
+      for (int i = ptid; i <= da.y; i += 32 * kWsProducerWarps) {
+        ws_cp4(st + sm.re + 4 * i, p.eptr + da.x + i);
+        if (i < da.y) ws_cp4(st + sm.rid + 4 * i, p.rows + da.x + i);
+      }
+      for (int e = 2 * ptid; e < db.y; e += 64 * kWsProducerWarps) ws_cp16(st + sm.ent + 8 * e, ent + db.x + e);
+      if (ptid < 2)
+        ws_cp16(st + sm.desc + 16 * ptid,
+                reinterpret_cast<const int4*>(p.tile_desc) + 2 * ((blockIdx.x + j * (int)gridDim.x) % T) + ptid);
+      ws_cp_arrive(full0 + 8 * slot);
+      cp_async_commit();
+      da = na; db = nbq; na = fa; nbq = fb;
+    }
+    cp_async_wait<0>();
+    return;
+  }
+
+  // --------------------------------------------------------------------------------------------- consumers
+  constexpr int L = LC >= 8 ? LC / 2 : LC;
+  constexpr int WPL = LC >= 8 ? 2 : 1;
+  constexpr int kGroups = kWsConsumerWarps * 32 / L;
+  const int ctid = tid - 32 * kWsProducerWarps;
+  const int gl = ctid & (L - 1), grp = ctid / L;
+  const bool live0 = gl < words, live1 = WPL == 2 && gl + L < words;
+  const uint32_t woff0 = live0 ? gl * 16 : 0, woff1 = live1 ? (gl + L) * 16 : 0;
+  float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f), bv1 = bv0;
+  if (bias && live0) bv0 = ldg4(bias + gl * 4);
+  if (bias && live1) bv1 = ldg4(bias + (gl + L) * 4);
+  const float slope = prelu_slope ? __ldg(prelu_slope) : 0.f;
+
+  for (int i = 0; i < n_my; ++i) {
+    const int slot = i % kWsStages;
+    const int item = blockIdx.x + i * gridDim.x;
+    const int b0 = (item / T) * SB;
+    const int nb = min(SB, B - b0);
+    ws_wait_backoff(full0 + 8 * slot, (uint32_t)((i / kWsStages) & 1));
+    const unsigned char* st = smem + slot * sm.stage;
+    const int nr = *reinterpret_cast<const int*>(st + sm.desc + 4);
+    const int e0 = *reinterpret_cast<const int*>(st + sm.desc + 16);
+    const int32_t* re = reinterpret_cast<const int32_t*>(st + sm.re);
+    const int32_t* rid = reinterpret_cast<const int32_t*>(st + sm.rid);
+    const int2* en = reinterpret_cast<const int2*>(st + sm.ent);
+    const unsigned char* xb[SB];     // ragged last sample block: sample nb-1 stands in (its result is not stored)
+#pragma unroll
+    for (int s = 0; s < SB; ++s) xb[s] = st + sm.xs + (uint32_t)min(s, nb - 1) * sstride;
+    for (int r = grp; r < ((dbg & 2) ? 0 : nr); r += kGroups) {
+      const int le0 = re[r] - e0, le1 = re[r + 1] - e0;               // even count: rows are padded to pairs
+      float4 acc0[SB], acc1[SB];
+#pragma unroll
+      for (int s = 0; s < SB; ++s) acc0[s] = acc1[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll(SB * WPL >= 4 ? 1 : 2)
+      for (int le = le0; le < le1; le += 2) {
+        const int4 e2 = *reinterpret_cast<const int4*>(en + le);      // two entries {lidx (pads: zero row), w}
+        const uint32_t o0 = (uint32_t)e2.x * rowb, o1 = (uint32_t)e2.z * rowb;
+        const float w0 = __int_as_float(e2.y), w1 = __int_as_float(e2.w);
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+          const float4 va = *reinterpret_cast<const float4*>(xb[s] + o0 + woff0);
+          const float4 vb = *reinterpret_cast<const float4*>(xb[s] + o1 + woff0);
+          fma4_packed(acc0[s], w0, va);
+          fma4_packed(acc0[s], w1, vb);
+          if (WPL == 2) {
+            const float4 vc = *reinterpret_cast<const float4*>(xb[s] + o0 + woff1);
+            const float4 vd = *reinterpret_cast<const float4*>(xb[s] + o1 + woff1);
+            fma4_packed(acc1[s], w0, vc);
+            fma4_packed(acc1[s], w1, vd);
+          }
+        }
+      }
+      const int64_t row = rid[r];
+#pragma unroll
+      for (int s = 0; s < SB; ++s) {
+        if (s >= nb) break;
+        const int64_t o = (int64_t)(b0 + s) * out_bstride + row * C;
+        if (live0) {
+          float4 a = make_float4(acc0[s].x + bv0.x, acc0[s].y + bv0.y, acc0[s].z + bv0.z, acc0[s].w + bv0.w);
+          if (z_out) st4(z_out + o + gl * 4, a);
+          if (prelu_slope)
+            a = make_float4(prelu_f(a.x, slope), prelu_f(a.y, slope), prelu_f(a.z, slope), prelu_f(a.w, slope));
+          st4(out + o + gl * 4, a);
+        }
+        if (live1) {
+          float4 a = make_float4(acc1[s].x + bv1.x, acc1[s].y + bv1.y, acc1[s].z + bv1.z, acc1[s].w + bv1.w);
+          if (z_out) st4(z_out + o + (gl + L) * 4, a);
+          if (prelu_slope)
+            a = make_float4(prelu_f(a.x, slope), prelu_f(a.y, slope), prelu_f(a.z, slope), prelu_f(a.w, slope));
+          st4(out + o + (gl + L) * 4, a);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ws_arrive(empty0 + 8 * slot);                     // this warp is done with the stage
+  }
+}
+
+// Rows with more entries than a tile may hold: one CTA per (row, sample); warp w takes entries beg + w, beg + w + 8,
+// ... (a fixed assignment), the 8 partial rows are summed in warp order -> deterministic, no atomics.
+__global__ void __launch_bounds__(256)
+    spmm_heavy_kernel(const int32_t* __restrict__ heavy_rows, const int32_t* __restrict__ rowptr,
+                      const int32_t* __restrict__ col, const float* __restrict__ w, const float* __restrict__ x,
+                      float* __restrict__ out, int64_t n_in, int C, int64_t x_bstride, int64_t out_bstride,
+                      const float* __restrict__ bias, const float* __restrict__ prelu_slope, float* __restrict__ z_out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float4* part = reinterpret_cast<float4*>(smem);          // [8][words]
+  const int words = C >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = heavy_rows[blockIdx.x];
+  const int b = blockIdx.y;
+  const int32_t beg = rowptr[row], end = rowptr[row + 1];
+  const float* xb = x + (int64_t)b * x_bstride;
+  for (int w0 = 0; w0 < words; w0 += 32) {
+    const int wd = w0 + lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (wd < words) {
+#pragma unroll 4
+      for (int32_t k = beg + warp; k < end; k += 8) {
+        const int32_t c = __ldg(col + k);
+        if (c < n_in) fma4(acc, w ? __ldg(w + k) : 1.f, ldg4(xb + (int64_t)c * C + wd * 4));
+      }
+      part[warp * words + wd] = acc;
+    }
+  }
+  __syncthreads();
+  const float slope = prelu_slope ? __ldg(prelu_slope) : 0.f;
+  for (int wd = threadIdx.x; wd < words; wd += 256) {
+    float4 a = part[wd];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      const float4 t = part[q * words + wd];
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    if (bias) {
+      const float4 bv = ldg4(bias + wd * 4);
+      a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+    }
+    const int64_t o = (int64_t)b * out_bstride + row * C + wd * 4;
+    if (z_out) st4(z_out + o, a);
+    if (prelu_slope) a = make_float4(prelu_f(a.x, slope), prelu_f(a.y, slope), prelu_f(a.z, slope), prelu_f(a.w, slope));
+    st4(out + o, a);
+  }
+}
+
+// samples per CTA: as many as keep the staged rows within ~64 KB (three CTAs per SM) and <= 4
+inline int tile_pick_sb(const TileArgs& p, int64_t C, int64_t B) {
+  static const int cap = getenv("GCL_TILE_SB") ? atoi(getenv("GCL_TILE_SB")) : 4;
+  static const int64_t budget = getenv("GCL_TILE_SMEM_KB") ? atoll(getenv("GCL_TILE_SMEM_KB")) << 10 : (64 << 10);
+  int sb = cap;
+  while (sb > 1 && (sb > B || (int64_t)sb * p.max_union * C * 4 > budget)) sb >>= 1;
+  return sb;
+}
+
+struct TileCall {
+  const float *w, *x;
+  float* out;
+  int C;
+  int64_t xbs, obs;
+  int B;
+  const float *bias, *slope;
+  float* z_out;
+  int64_t wbs;
+  float wsc;
+  const float *a_src, *a_dst;
+  int64_t abs_;
+  float neg;
+  float *alpha_csr, *alpha_pyg;
+  const int32_t* perm;
+  int64_t nnz;
+};
+
+template <int L, int SB, int MODE>
+int tile_launch(const gcl_tile_plan* plan, const TileCall& c, cudaStream_t s, const char* what) {
+  const TileArgs p = tile_args(plan);
+  const TileSmem sm = tile_smem(p, c.C, SB, MODE == 0 ? 1 : SB, MODE == 2);
+  if (sm.total > 227 * 1024) {
+    set_error("%s: tile needs %zu bytes of shared memory", what, sm.total);
+    return GCL_ERR_UNSUPPORTED;
+  }
+  auto kern = spmm_tile_kernel<L, SB, MODE>;
+  static bool attr_set = false;               // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail_cuda(e, what);
+    attr_set = true;
+  }
+  dim3 grid((unsigned)plan->n_tiles, (unsigned)ceil_div(c.B, SB));
+  kern<<<grid, kTileThreads, sm.total, s>>>(p, sm, c.w, c.x, c.out, c.C, c.xbs, c.obs, c.B, c.bias, c.slope, c.z_out,
+                                            c.wbs, c.wsc, c.a_src, c.a_dst, c.abs_, c.neg, c.alpha_csr, c.alpha_pyg,
+                                            c.perm, c.nnz);
+  GCL_CHECK_LAUNCH(what);
+  return GCL_OK;
+}
+
+template <int L, int MODE>
+int tile_dispatch_sb(int sb, const gcl_tile_plan* plan, const TileCall& c, cudaStream_t s, const char* what) {
+  if (sb >= 4) return tile_launch<L, 4, MODE>(plan, c, s, what);
+  if (sb >= 2) return tile_launch<L, 2, MODE>(plan, c, s, what);
+  return tile_launch<L, 1, MODE>(plan, c, s, what);
+}
+
+template <int MODE>
+int tile_dispatch(const gcl_tile_plan* plan, const TileCall& c, cudaStream_t s, const char* what) {
+  const int sb = tile_pick_sb(tile_args(plan), c.C, c.B);
+  const int words = c.C / 4;
+  if (words <= 4) return tile_dispatch_sb<4, MODE>(sb, plan, c, s, what);
+  if (words <= 8) return tile_dispatch_sb<8, MODE>(sb, plan, c, s, what);
+  if (words <= 16) return tile_dispatch_sb<16, MODE>(sb, plan, c, s, what);
+  return tile_dispatch_sb<32, MODE>(sb, plan, c, s, what);
+}
+
+template <int LC, int SB>
+int ws_launch(const gcl_tile_plan* plan, const int2* ent, const float* x, float* out, int C, int64_t xbs, int64_t obs,
+              int B, const float* bias, const float* slope, float* z_out, cudaStream_t s) {
+  const TileArgs p = tile_args(plan);
+  const WsSmem sm = ws_smem(p, C, SB);
+  auto kern = spmm_ws_kernel<LC, SB>;
+  static bool attr_set = false;               // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail_cuda(e, "gcl_spmm_tiled_f32");
+    attr_set = true;
+  }
+  const int64_t n_items = (int64_t)plan->n_tiles * ceil_div(B, SB);
+  static const int ctas = getenv("GCL_TILE_CTAS") ? atoi(getenv("GCL_TILE_CTAS")) : kNumSMs;
+  const unsigned grid = (unsigned)std::min<int64_t>(n_items, ctas);
+  static const int dbg = getenv("GCL_TILE_DBG") ? atoi(getenv("GCL_TILE_DBG")) : 0;   // elimination runs (wrong results)
+  kern<<<grid, kWsThreads, sm.total, s>>>(p, sm, ent, x, out, C, xbs, obs, B, (int)n_items, bias, slope, z_out, dbg);
+  GCL_CHECK_LAUNCH("gcl_spmm_tiled_f32");
+  return GCL_OK;
+}
+
+template <int LC>
+int ws_dispatch_l(const gcl_tile_plan* plan, const int2* ent, const float* x, float* out, int C, int64_t xbs,
+                  int64_t obs, int B, const float* bias, const float* slope, float* z_out, cudaStream_t s) {
+  const TileArgs p = tile_args(plan);
+  static const int sb_cap = getenv("GCL_TILE_SB") ? atoi(getenv("GCL_TILE_SB")) : 4;
+  int sb = sb_cap;
+  while (sb > 1 && (sb > B || ws_smem(p, C, sb).total > 227 * 1024)) sb >>= 1;
+  if (ws_smem(p, C, sb).total > 227 * 1024) {
+    set_error("gcl_spmm_tiled_f32: a tile (union %d rows of %d channels) does not fit the shared-memory ring",
+              p.max_union, C);
+    return GCL_ERR_UNSUPPORTED;
+  }
+  if (sb == 4) return ws_launch<LC, 4>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
+  if (sb == 2) return ws_launch<LC, 2>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
+  return ws_launch<LC, 1>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
+}
+
+int pipe_dispatch(const gcl_tile_plan* plan, const int2* ent, const float* x, float* out, int C, int64_t xbs,
+                  int64_t obs, int B, const float* bias, const float* slope, float* z_out, cudaStream_t s) {
+  const int words = C / 4;
+  if (words <= 4) return ws_dispatch_l<4>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
+  if (words <= 8) return ws_dispatch_l<8>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
+  if (words <= 16) return ws_dispatch_l<16>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
+  return ws_dispatch_l<32>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_plan(const gcl_tile_plan* plan, const char* what) {
+  GCL_CHECK_ARG(plan, "%s: null plan", what);
+  GCL_CHECK_ARG(plan->n_tiles == 0 || (plan->tile_rowptr && plan->tile_uptr && plan->rows && plan->eptr && plan->ek &&
+                                       plan->usrc && plan->lidx),
+                "%s: plan with null arrays", what);
+  GCL_CHECK_ARG(plan->n_tiles >= 0 && plan->n_heavy >= 0 && plan->max_rows >= 0 && plan->max_union >= 0 &&
+                    plan->max_entries >= 0 && plan->max_union < 0xFFFF,
+                "%s: bad plan sizes", what);
+  return GCL_OK;
+}
+
+}  // namespace
+}  // namespace gcl
+
+using namespace gcl;
+
+extern "C" int gcl_tile_plan_host(const int32_t* rowptr, const int32_t* col, const int32_t* order, int64_t n_rows,
+                                  int64_t n_rows_out, int64_t n_rows_in, int32_t max_rows, int32_t max_union,
+                                  int32_t max_entries, int32_t pad_entries, int32_t* tile_rowptr, int32_t* tile_uptr,
+                                  int32_t* rows, int32_t* eptr, uint16_t* lidx, int32_t* ek, int32_t* usrc,
+                                  int32_t* heavy_rows, int32_t* tile_desc, int64_t* counts) {
+  GCL_CHECK_ARG(rowptr && col && tile_rowptr && tile_uptr && rows && eptr && lidx && ek && usrc && heavy_rows &&
+                    tile_desc && counts,
+                "gcl_tile_plan_host: null pointer argument");
+  GCL_CHECK_ARG(n_rows >= 0 && n_rows_out >= 0 && n_rows_out <= n_rows && n_rows_in > 0 && max_rows > 0 &&
+                    max_union > 0 && max_union < 0xFFFF && max_entries >= max_union + 3 &&
+                    (pad_entries == 1 || pad_entries == 2 || pad_entries == 4),
+                "gcl_tile_plan_host: bad sizes");
+  const size_t ncol = (size_t)std::max<int64_t>(n_rows_in, 1);
+  // stamp[c] == T: column c is in the current tile's union, numbered local[c]; rstamp marks the columns of the row
+  // under consideration (distinct count)
+  std::vector<int64_t> stamp(ncol, -1), rstamp(ncol, -1);
+  std::vector<int32_t> local(ncol, 0);
+  int64_t T = 0, nplan = 0, nu_total = 0, ne_total = 0, nheavy = 0;
+  int cur_rows = 0, cur_u = 0, cur_e = 0, mr = 0, mu = 0, me = 0;
+  tile_rowptr[0] = 0;
+  tile_uptr[0] = 0;
+  eptr[0] = 0;
+  auto close_tile = [&]() {
+    if (cur_rows == 0) return;
+    mr = std::max(mr, cur_rows); mu = std::max(mu, cur_u); me = std::max(me, cur_e);
+    int32_t* d = tile_desc + 8 * T;
+    d[0] = tile_rowptr[T]; d[1] = cur_rows; d[2] = tile_uptr[T]; d[3] = cur_u;
+    d[4] = eptr[tile_rowptr[T]]; d[5] = cur_e; d[6] = d[7] = 0;
+    ++T;                                        // stamps of the closed tile become stale
+    tile_rowptr[T] = (int32_t)nplan;
+    tile_uptr[T] = (int32_t)nu_total;
+    cur_rows = cur_u = cur_e = 0;
+  };
+  for (int64_t q = 0; q < n_rows; ++q) {
+    const int64_t r = order ? order[q] : q;
+    GCL_CHECK_ARG(r >= 0 && r < n_rows, "gcl_tile_plan_host: order[%lld] = %lld out of range", (long long)q, (long long)r);
+    if (r >= n_rows_out) continue;
+    const int32_t beg = rowptr[r], end = rowptr[r + 1];
+    const int len = end - beg;
+    const int plen = (len + pad_entries - 1) / pad_entries * pad_entries;     // padded entry count of the row
+    int distinct = 0, add = 0;                  // distinct sources of the row / those not yet in the tile's union
+    for (int32_t k = beg; k < end; ++k) {
+      const int32_t c = col[k];
+      if (c >= n_rows_in || rstamp[c] == q) continue;
+      rstamp[c] = q;
+      ++distinct;
+      add += stamp[c] != T;
+    }
+    if (distinct > max_union || plen > max_entries) {
+      heavy_rows[nheavy++] = (int32_t)r;
+      continue;
+    }
+    if (cur_rows == max_rows || cur_u + add > max_union || cur_e + plen > max_entries) close_tile();
+    rows[nplan] = (int32_t)r;
+    for (int32_t k = beg; k < end; ++k) {
+      const int32_t c = col[k];
+      uint16_t li = kMasked;
+      if (c < n_rows_in) {
+        if (stamp[c] != T) {
+          stamp[c] = T;
+          local[c] = cur_u++;
+          usrc[nu_total++] = c;
+        }
+        li = (uint16_t)local[c];
+      }
+      lidx[ne_total] = li;
+      ek[ne_total] = k;
+      ++ne_total;
+    }
+    for (int q2 = len; q2 < plen; ++q2) {       // padding: counts as a zero row with weight 0
+      lidx[ne_total] = kMasked;
+      ek[ne_total] = -1;
+      ++ne_total;
+    }
+    cur_e += plen;
+    ++cur_rows;
+    ++nplan;
+    eptr[nplan] = (int32_t)ne_total;
+  }
+  close_tile();
+  counts[0] = T; counts[1] = nplan; counts[2] = nu_total; counts[3] = ne_total; counts[4] = nheavy;
+  counts[5] = mr; counts[6] = mu; counts[7] = me;
+  return GCL_OK;
+}
+
+extern "C" int gcl_spmm_tiled_f32(const gcl_tile_plan* plan, const int32_t* ent, const int32_t* rowptr,
+                                  const int32_t* col, const float* w, const float* x, float* out, int64_t batch,
+                                  int64_t n_rows_in, int64_t channels, int64_t x_bstride, int64_t out_bstride,
+                                  const float* bias, const float* prelu_slope, float* z_out, void* stream) {
+  if (int rc = check_plan(plan, "gcl_spmm_tiled_f32")) return rc;
+  GCL_CHECK_ARG(rowptr && col && x && out && x != out, "gcl_spmm_tiled_f32: null or aliased pointer argument");
+  GCL_CHECK_ARG(plan->n_tiles == 0 || (ent && plan->tile_desc && al16(ent) && al16(plan->tile_desc)),
+                "gcl_spmm_tiled_f32: the packed entries / tile descriptors are missing or not 16-byte aligned");
+  GCL_CHECK_ARG(plan->pad_entries == 2 || plan->pad_entries == 4 || plan->n_tiles == 0,
+                "gcl_spmm_tiled_f32: the plan must be built with pad_entries = 2 or 4");
+  GCL_CHECK_ARG(channels > 0 && channels % 4 == 0 && channels <= 128 && x_bstride % 4 == 0 && out_bstride % 4 == 0 &&
+                    al16(x) && al16(out) && (!bias || al16(bias)) && (!z_out || al16(z_out)),
+                "gcl_spmm_tiled_f32: needs 16-byte aligned rows of 4..128 channels (multiple of 4); use gcl_spmm_f32");
+  GCL_CHECK_ARG(batch >= 0 && batch <= 65535 && n_rows_in > 0, "gcl_spmm_tiled_f32: bad sizes");
+  GCL_CHECK_ARG(n_rows_in * channels < (1ll << 31), "gcl_spmm_tiled_f32: one sample's features must index with 31 bits");
+  if (batch == 0) return GCL_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (plan->n_tiles > 0) {
+    if (int rc = pipe_dispatch(plan, reinterpret_cast<const int2*>(ent), x, out, (int)channels, x_bstride, out_bstride,
+                               (int)batch, bias, prelu_slope, z_out, s))
+      return rc;
+  }
+  if (plan->n_heavy > 0) {
+    GCL_CHECK_ARG(plan->heavy_rows, "gcl_spmm_tiled_f32: plan lists heavy rows but has no heavy_rows array");
+    dim3 grid((unsigned)plan->n_heavy, (unsigned)batch);
+    spmm_heavy_kernel<<<grid, 256, 8 * channels * 4, s>>>(plan->heavy_rows, rowptr, col, w, x, out, n_rows_in,
+                                                           (int)channels, x_bstride, out_bstride, bias, prelu_slope,
+                                                           z_out);
+    GCL_CHECK_LAUNCH("gcl_spmm_tiled_f32(heavy rows)");
+  }
+  return GCL_OK;
+}
+
+extern "C" int gcl_gat_fwd_tiled_f32(const gcl_tile_plan* plan, const int32_t* perm, const float* z, const float* a_src,
+                                     const float* a_dst, const float* bias, float* out, float* alpha_csr,
+                                     float* alpha_pyg, const float* prelu_slope, float* z_out, int64_t batch,
+                                     int64_t n_nodes, int64_t nnz, int64_t c, float negative_slope, void* stream) {
+  if (int rc = check_plan(plan, "gcl_gat_fwd_tiled_f32")) return rc;
+  GCL_CHECK_ARG(z && a_src && a_dst && out && alpha_csr && z != out, "gcl_gat_fwd_tiled_f32: null pointer argument");
+  GCL_CHECK_ARG(!alpha_pyg || perm, "gcl_gat_fwd_tiled_f32: alpha_pyg needs perm");
+  GCL_CHECK_ARG(plan->n_heavy == 0, "gcl_gat_fwd_tiled_f32: plan has heavy rows; use gcl_gat_fwd_f32");
+  GCL_CHECK_ARG(c > 0 && c % 4 == 0 && c <= 128 && al16(z) && al16(out) && (!bias || al16(bias)) &&
+                    (!z_out || al16(z_out)),
+                "gcl_gat_fwd_tiled_f32: needs 16-byte aligned rows of 4..128 channels (multiple of 4)");
+  GCL_CHECK_ARG(batch >= 0 && batch <= 65535 && n_nodes >= 0 && nnz >= 0, "gcl_gat_fwd_tiled_f32: bad sizes");
+  if (batch == 0 || n_nodes == 0 || plan->n_tiles == 0) return GCL_OK;
+  TileCall cl{nullptr, z, out, (int)c, n_nodes * c, n_nodes * c, (int)batch, bias, prelu_slope, z_out, 0, 1.f,
+              a_src, a_dst, n_nodes, negative_slope, alpha_csr, alpha_pyg, perm, nnz};
+  return tile_dispatch<2>(plan, cl, static_cast<cudaStream_t>(stream), "gcl_gat_fwd_tiled_f32");
+}

@@ -21,6 +21,10 @@ _PROTOS = {
     "gcl_csr_build": (c_int, [P, P, I64, I64, I32, P, P, P, P, P, P, P, P, P, P, P, SZ, P]),
     "gcl_csr_weights": (c_int, [P, P, P, P, P, I64, I64, I32, P, P, P, P]),
     "gcl_spmm_f32": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, I64, P, P, P, I64, P]),
+    "gcl_tile_plan_host": (c_int, [P, P, P, I64, I64, I64, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P]),
+    "gcl_spmm_tiled_f32": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, I64, P, P, P, P]),
+    "gcl_gat_fwd_tiled_f32": (c_int, [P] * 11 + [I64, I64, I64, I64, F32, P]),
+    "gcl_gat_bwd_tiled_f32": (c_int, [P] * 14 + [I64, I64, I64, I64, F32, P]),
     "gcl_linear_fwd_f32": (c_int, [P, P, P, P, I64, I64, I64, P, P, P, P]),
     "gcl_linear_fwd_scores_f32": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, P, P]),
     "gcl_linear_bwd_dx_f32": (c_int, [P, P, P, I64, I64, I64, P, P]),
@@ -59,10 +63,22 @@ _PROTOS = {
     "gcl_adam_f32": (c_int, [P, P, P, P, I64, F32, F32, F32, F32, F32, P, P]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+
+
+class TilePlanStruct(ctypes.Structure):
+    """gcl_tile_plan of include/gcl_b200.h: device arrays of one tile plan (host struct, passed by pointer)."""
+    _fields_ = [("tile_rowptr", c_void_p), ("tile_uptr", c_void_p), ("rows", c_void_p), ("eptr", c_void_p),
+                ("lidx", c_void_p), ("ek", c_void_p), ("usrc", c_void_p), ("heavy_rows", c_void_p),
+                ("tile_desc", c_void_p),
+                ("n_tiles", ctypes.c_int32), ("n_heavy", ctypes.c_int32), ("max_rows", ctypes.c_int32),
+                ("max_union", ctypes.c_int32), ("max_entries", ctypes.c_int32), ("pad_entries", ctypes.c_int32)]
 
 
 def lib_path() -> str:
+    override = os.environ.get("GCL_LIB_PATH")          # development: A/B builds of the kernels
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 

@@ -5,10 +5,13 @@ sites /root/reference/src/models.py:414,419,425,431).  Here that work happens on
 (edge_index, num_nodes, flavour) and is cached; SparseGATConv's pruned edge lists
 (models.py:148, 846) are new tensors and therefore get their own entry.
 """
+import ctypes
+import os
 import weakref
 from collections import OrderedDict
 from typing import Optional
 
+import numpy as np
 import torch
 
 from . import _cabi
@@ -24,6 +27,85 @@ def _stream() -> int:
 def _require_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"gcl_b200: {what} must be a CUDA tensor (got {t.device}); there is no CPU fallback")
+
+
+# Row orders with spatial locality, keyed by node count: tiles of a plan take rows in this order, which keeps the
+# union of their source rows small.  The model registers the orders it knows from the mesh geometry (graphs_build);
+# graphs without a hint are tiled in natural row order.  Purely a scheduling hint -- results do not depend on it.
+ORDER_HINTS = {}
+
+TILE_ROWS = int(os.environ.get("GCL_TILE_ROWS", "64"))
+TILE_UNION = int(os.environ.get("GCL_TILE_UNION", "128"))
+TILE_ENTRIES = int(os.environ.get("GCL_TILE_ENTRIES", "1024"))
+TILED = os.environ.get("GCL_TILED", "1") != "0"          # A/B switch: 0 = first-generation row-gather kernels
+
+
+class TilePlan:
+    """Tile plan of one CSR orientation (gcl_tile_plan_host): device index arrays + the C struct that names them.
+    pad = 2: rows padded to entry pairs, as the pipelined SpMM kernel wants; pad = 1 for the attention kernels."""
+
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, nnz: int, n_rows: int, n_rows_out: int,
+                 n_rows_in: int, order: Optional[np.ndarray] = None, max_rows: int = None, max_union: int = None,
+                 max_entries: int = None, pad: int = 2):
+        lib = _cabi.load()
+        dev = rowptr.device
+        rp = np.ascontiguousarray(rowptr.cpu().numpy(), dtype=np.int32)
+        co = np.ascontiguousarray(col[: max(nnz, 1)].cpu().numpy(), dtype=np.int32)
+        od = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+        if od is not None and od.shape != (n_rows,):
+            raise ValueError(f"gcl_b200: row order hint has shape {od.shape}, graph has {n_rows} rows")
+        n1, ne = n_rows + 1, max(nnz, 1) + (pad - 1) * n_rows
+        out = dict(tile_rowptr=np.zeros(n1, np.int32), tile_uptr=np.zeros(n1, np.int32), rows=np.zeros(n1, np.int32),
+                   eptr=np.zeros(n1, np.int32), lidx=np.zeros(ne, np.uint16), ek=np.zeros(ne, np.int32),
+                   usrc=np.zeros(max(nnz, 1), np.int32), heavy_rows=np.zeros(n1, np.int32),
+                   tile_desc=np.zeros(8 * n1, np.int32))
+        counts = np.zeros(8, np.int64)
+        ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        rc = lib.gcl_tile_plan_host(ptr(rp), ptr(co), None if od is None else ptr(od), n_rows, n_rows_out, n_rows_in,
+                                    max_rows or TILE_ROWS, max_union or TILE_UNION, max_entries or TILE_ENTRIES, pad,
+                                    ptr(out["tile_rowptr"]), ptr(out["tile_uptr"]), ptr(out["rows"]), ptr(out["eptr"]),
+                                    ptr(out["lidx"]), ptr(out["ek"]), ptr(out["usrc"]), ptr(out["heavy_rows"]),
+                                    ptr(out["tile_desc"]), ptr(counts))
+        _cabi.check(rc, "gcl_tile_plan_host")
+        T, nplan, nu, nent, nheavy, mr, mu, me = (int(v) for v in counts)
+        self.n_tiles, self.n_plan_rows, self.n_union, self.n_entries, self.n_heavy = T, nplan, nu, nent, nheavy
+        self.max_rows, self.max_union, self.max_entries, self.pad = mr, mu, me, pad
+        used = dict(tile_rowptr=T + 1, tile_uptr=T + 1, rows=max(nplan, 1), eptr=nplan + 1, lidx=max(nent, 1),
+                    ek=max(nent, 1), usrc=max(nu, 1), heavy_rows=max(nheavy, 1), tile_desc=8 * max(T, 1))
+        self.t = {}
+        for k, n in used.items():
+            a = out[k][:n]
+            if a.dtype == np.uint16:                  # torch has no uint16 arithmetic; the kernels only need the bytes
+                a = a.view(np.int16)
+            self.t[k] = torch.from_numpy(a.copy()).to(dev)
+        self.struct = _cabi.TilePlanStruct(*(self.t[k].data_ptr() for k in
+                                             ("tile_rowptr", "tile_uptr", "rows", "eptr", "lidx", "ek", "usrc",
+                                              "heavy_rows", "tile_desc")), T, nheavy, mr, mu, me, pad)
+        self.ref = ctypes.byref(self.struct)
+        self._ent = {}
+
+    @property
+    def union_per_row(self) -> float:
+        return self.n_union / max(self.n_plan_rows, 1)
+
+    def entries(self, w: Optional[torch.Tensor], key=None) -> torch.Tensor:
+        """int32 [n_entries, 2] = {lidx, weight bits} in plan order for per-CSR-entry weights w (None = 1); pad and
+        masked entries carry lidx = max_union (the kernel's all-zero row), pads weight 0.  Cached per `key` (the weight kind); the gather w[ek] runs once."""
+        hit = self._ent.get(key) if key is not None else None
+        if hit is not None:
+            return hit
+        ek = self.t["ek"].long()
+        real = ek >= 0
+        if w is None:
+            wv = real.to(torch.float32)
+        else:
+            wv = torch.where(real, w.to(torch.float32)[ek.clamp_min(0)], torch.zeros((), device=ek.device))
+        li = self.t["lidx"].to(torch.int32) & 0xFFFF
+        li = torch.where(li == 0xFFFF, torch.full_like(li, self.max_union), li)   # pads / masked -> the zero row
+        ent = torch.stack([li, wv.view(torch.int32)], dim=1).contiguous()
+        if key is not None:
+            self._ent[key] = ent
+        return ent
 
 
 class CSRGraph:
@@ -74,6 +156,22 @@ class CSRGraph:
         self.max_in_degree = int((self.rowptr[1:] - self.rowptr[:-1]).max()) if N > 0 else 0
         self._weights = {}
         self._ei_view = None
+        self._plans = {}
+
+    def plan(self, transposed: bool = False, n_rows_out: Optional[int] = None,
+             n_rows_in: Optional[int] = None, pad: int = 2) -> TilePlan:
+        """Tile plan of the receiver-grouped (forward) or sender-grouped (backward) CSR, built once and cached.
+        n_rows_out: only rows below it are produced; n_rows_in: columns at or past it are masked (zero rows);
+        pad: 2 for the SpMM kernel (entry pairs), 1 for the attention kernels."""
+        n = self.num_nodes
+        key = (bool(transposed), n if n_rows_out is None else int(n_rows_out),
+               n if n_rows_in is None else int(n_rows_in), int(pad))
+        pl = self._plans.get(key)
+        if pl is None:
+            rp, co = (self.rowptr_t, self.col_t) if transposed else (self.rowptr, self.col)
+            pl = TilePlan(rp, co, self.nnz, n, key[1], key[2], ORDER_HINTS.get(n), pad=pad)
+            self._plans[key] = pl
+        return pl
 
     @property
     def edge_index_with_loops(self) -> torch.Tensor:

@@ -112,6 +112,20 @@ def _max_edge(verts: np.ndarray, faces: np.ndarray):
     return np.linalg.norm(verts[s] - verts[r], axis=-1).max()
 
 
+def morton_order(xyz: np.ndarray) -> np.ndarray:
+    """Permutation that sorts points of the unit sphere along a 3-d Morton (Z-order) curve, int32 [n]."""
+    q = np.clip(((np.asarray(xyz, dtype=np.float64) + 1.0) * 0.5 * 1023.0).astype(np.int64), 0, 1023)
+
+    def spread(v):
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    return np.argsort(code, kind="stable").astype(np.int32)
+
+
 # ------------------------------------------------------------------------------------------ searches (device)
 def _stream():
     return torch.cuda.current_stream().cuda_stream
@@ -181,3 +195,9 @@ class ModelGraphs:
         self.init_grid_features = torch.as_tensor(_static_features(glat.reshape(-1), glon.reshape(-1)), device=device)
         mlat, mlon = _mesh_lat_lon(verts)
         self.init_mesh_features = torch.as_tensor(_static_features(mlat, mlon), device=device)
+        # scheduling hints for the tiled aggregation kernels: mesh rows along a space-filling curve (grid rows are
+        # already lat-major), so that a tile's rows share most of their neighbours
+        from . import graph as _graph
+        order = morton_order(verts)
+        _graph.ORDER_HINTS[self.num_mesh] = order
+        _graph.ORDER_HINTS[G + self.num_mesh] = np.concatenate([np.arange(G, dtype=np.int32), G + order]).astype(np.int32)

@@ -8,6 +8,7 @@ from typing import Optional
 import torch
 
 from . import _cabi
+from . import graph as _graph
 from .graph import CSRGraph, NORM_GCN, NORM_MEAN, NORM_NONE  # noqa: F401
 
 
@@ -78,15 +79,29 @@ def _as3(x: torch.Tensor):
 
 
 # ------------------------------------------------------------------------------------------- raw calls
-def spmm_raw(rowptr, col, w, x3, n_out, bias=None, slope=None, want_z=False):
+def _tileable(C: int, *tensors) -> bool:
+    """The tiled kernels take 16-byte aligned rows of 4..128 channels (a multiple of 4)."""
+    return (_graph.TILED and C % 4 == 0 and 0 < C <= 128
+            and all(t is None or t.data_ptr() % 16 == 0 for t in tensors))
+
+
+def spmm_raw(rowptr, col, w, x3, n_out, bias=None, slope=None, want_z=False, plan=None, wkey=None):
+    """plan: a graph.TilePlan (pad = 2) of (rowptr, col) built for n_rows_out = n_out and n_rows_in = x3.shape[1]: the
+    tiled kernel (persistent CTAs, rows staged in a shared-memory ring by asynchronous copies); otherwise the
+    row-gather kernel.  wkey: cache key of the plan-ordered copy of w (the weight kind)."""
     B, n_in, C = x3.shape
     out = torch.empty((B, n_out, C), dtype=torch.float32, device=x3.device)
     z = torch.empty_like(out) if want_z else None
     with torch.cuda.device(x3.device):
         nnz = int(col.numel())
         nbytes = 4 * B * C * (n_in + n_out * (2 if want_z else 1)) + nnz * (8 if w is not None else 4) + 4 * (n_out + 1)
-        _call("gcl_spmm_f32", _p(rowptr), _p(col), _p(w), _p(x3), _p(out), B, n_out, n_in, C, n_in * C, n_out * C,
-              _p(bias), _p(slope), _p(z), nnz, _stream(), nbytes=nbytes, tag=f"N{n_out}xC{C}xB{B}")
+        if plan is not None and _tileable(C, x3, out, bias, z):
+            ent = plan.entries(w, wkey)
+            _call("gcl_spmm_tiled_f32", plan.ref, _p(ent), _p(rowptr), _p(col), _p(w), _p(x3), _p(out), B, n_in, C,
+                  n_in * C, n_out * C, _p(bias), _p(slope), _p(z), _stream(), nbytes=nbytes, tag=f"N{n_out}xC{C}xB{B}")
+        else:
+            _call("gcl_spmm_f32", _p(rowptr), _p(col), _p(w), _p(x3), _p(out), B, n_out, n_in, C, n_in * C, n_out * C,
+                  _p(bias), _p(slope), _p(z), nnz, _stream(), nbytes=nbytes, tag=f"N{n_out}xC{C}xB{B}")
     return out, z
 
 
@@ -201,7 +216,8 @@ class _Aggregate(torch.autograd.Function):
         slope_c = _chk(slope, "slope") if slope is not None else None
         w, _ = graph.weights(kind)
         need_z = slope_c is not None and any(ctx.needs_input_grad[:3])
-        out, z = spmm_raw(graph.rowptr, graph.col, w, x3, n_out, bias_c, slope_c, need_z)
+        plan = graph.plan(False, n_out, graph.num_nodes) if _tileable(x3.shape[-1]) else None
+        out, z = spmm_raw(graph.rowptr, graph.col, w, x3, n_out, bias_c, slope_c, need_z, plan, ("fwd", kind))
         ctx.graph, ctx.kind, ctx.squeeze = graph, kind, squeeze
         ctx.has_bias, ctx.has_slope = bias is not None, slope is not None
         ctx.save_for_backward(z, slope_c)
@@ -225,7 +241,8 @@ class _Aggregate(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             _, wt = g.weights(ctx.kind)
-            dx, _ = spmm_raw(g.rowptr_t, g.col_t, wt, d3, g.num_nodes)
+            plan = g.plan(True, g.num_nodes, d3.shape[1]) if _tileable(d3.shape[-1]) else None
+            dx, _ = spmm_raw(g.rowptr_t, g.col_t, wt, d3, g.num_nodes, plan=plan, wkey=("bwd", ctx.kind))
             if ctx.squeeze:
                 dx = dx.squeeze(0)
         return dx, dbias, (dslope if ctx.has_slope and ctx.needs_input_grad[2] else None), None, None, None
@@ -465,11 +482,21 @@ class _GAT(torch.autograd.Function):
             if scores is None:
                 _call("gcl_gat_scores_f32", _p(z3), _p(a_s), _p(a_d), _p(asrc), _p(adst), B * N, H, C, _stream(),
                       nbytes=4 * B * N * (H * C + 2 * H), tag=f"R{B * N}xH{H}xC{C}")
-            _call("gcl_gat_fwd_f32", _p(graph.rowptr), _p(graph.col), _p(graph.perm), _p(z3), _p(asrc), _p(adst),
-                  _p(bias_c), _p(out), _p(alpha), _p(alpha_pyg), _p(ps), _p(zpre), B, N, nnz, H, C, int(bool(concat)),
-                  float(slope),
-                  _stream(), nbytes=4 * B * (N * (H * C + cout + 2 * H) + nnz * H * (2 if want_alpha else 1)) + 4 * nnz
-                  + 4 * (N + 1), tag=f"N{N}xH{H}xC{C}xB{B}")
+            nbytes = (4 * B * (N * (H * C + cout + 2 * H) + nnz * H * (2 if want_alpha else 1)) + 4 * nnz
+                      + 4 * (N + 1))
+            plan = None
+            if H == 1 and nnz > 0 and _tileable(C, z3, out, bias_c, zpre):
+                plan = graph.plan(False, pad=1)
+                if plan.n_heavy:
+                    plan = None
+            if plan is not None:        # one kernel: coefficients + aggregation out of shared memory
+                _call("gcl_gat_fwd_tiled_f32", plan.ref, _p(graph.perm), _p(z3), _p(asrc), _p(adst), _p(bias_c),
+                      _p(out), _p(alpha), _p(alpha_pyg), _p(ps), _p(zpre), B, N, nnz, C, float(slope), _stream(),
+                      nbytes=nbytes, tag=f"N{N}xH{H}xC{C}xB{B}")
+            else:
+                _call("gcl_gat_fwd_f32", _p(graph.rowptr), _p(graph.col), _p(graph.perm), _p(z3), _p(asrc), _p(adst),
+                      _p(bias_c), _p(out), _p(alpha), _p(alpha_pyg), _p(ps), _p(zpre), B, N, nnz, H, C,
+                      int(bool(concat)), float(slope), _stream(), nbytes=nbytes, tag=f"N{N}xH{H}xC{C}xB{B}")
         ctx.graph, ctx.H, ctx.C, ctx.concat, ctx.slope = graph, H, C, bool(concat), float(slope)
         ctx.squeeze, ctx.has_bias, ctx.has_prelu = squeeze, bias is not None, ps is not None
         ctx.save_for_backward(z3, asrc, adst, alpha, a_s, a_d, zpre, ps)
@@ -503,11 +530,21 @@ class _GAT(torch.autograd.Function):
         nb = lib.gcl_gat_datt_workspace_bytes(B * N, H, C)
         ws = _ws(nb, dev)
         with torch.cuda.device(dev):
-            _call("gcl_gat_bwd_f32", _p(g.rowptr), _p(g.col), _p(g.rowptr_t), _p(g.col_t), _p(g.t2r), _p(z3),
-                  _p(asrc), _p(adst), _p(alpha), _p(a_s), _p(a_d), _p(d3), _p(gbuf), _p(da_s), _p(da_d), _p(dz),
-                  B, N, g.nnz, H, C, int(ctx.concat), ctx.slope, _stream(),
-                  nbytes=4 * B * (N * (2 * H * C + d3.shape[-1] + 4 * H) + 3 * g.nnz * H) + 16 * g.nnz,
-                  tag=f"N{N}xH{H}xC{C}xB{B}")
+            nbytes = 4 * B * (N * (2 * H * C + d3.shape[-1] + 4 * H) + 3 * g.nnz * H) + 16 * g.nnz
+            plans = None
+            if H == 1 and g.nnz > 0 and _tileable(C, z3, d3, dz, a_s, a_d):
+                plans = (g.plan(False, pad=1), g.plan(True, pad=1))
+                if plans[0].n_heavy or plans[1].n_heavy:
+                    plans = None
+            if plans is not None:
+                _call("gcl_gat_bwd_tiled_f32", plans[0].ref, plans[1].ref, _p(g.t2r), _p(z3), _p(asrc), _p(adst),
+                      _p(alpha), _p(a_s), _p(a_d), _p(d3), _p(gbuf), _p(da_s), _p(da_d), _p(dz), B, N, g.nnz, C,
+                      ctx.slope, _stream(), nbytes=nbytes, tag=f"N{N}xH{H}xC{C}xB{B}")
+            else:
+                _call("gcl_gat_bwd_f32", _p(g.rowptr), _p(g.col), _p(g.rowptr_t), _p(g.col_t), _p(g.t2r), _p(z3),
+                      _p(asrc), _p(adst), _p(alpha), _p(a_s), _p(a_d), _p(d3), _p(gbuf), _p(da_s), _p(da_d), _p(dz),
+                      B, N, g.nnz, H, C, int(ctx.concat), ctx.slope, _stream(), nbytes=nbytes,
+                      tag=f"N{N}xH{H}xC{C}xB{B}")
             _call("gcl_gat_datt_f32", _p(z3), _p(da_s), _p(da_d), _p(datt_s), _p(datt_d), B * N, H, C, _p(ws), nb,
                   _stream(), nbytes=4 * B * N * (H * C + 2 * H), tag=f"R{B * N}xH{H}xC{C}")
         dbias = colsum_raw(d3.view(-1, d3.shape[-1])) if ctx.has_bias else None

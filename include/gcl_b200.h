@@ -107,10 +107,63 @@ int gcl_spmm_f32(const int32_t* rowptr, const int32_t* col, const float* w, cons
                  int64_t nnz /* number of CSR entries, 0 = unknown (scheduling hint only) */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K2/K3/K6, tiled.  Same result as gcl_spmm_f32 (same per-row summation order), different schedule: the rows are
+ *   grouped into TILES (<= max_rows rows whose union of source rows has <= max_union members); a CTA stages the
+ *   union's feature rows in shared memory with asynchronous bulk copies (cp.async.bulk + mbarrier, no register
+ *   staging) and reduces the tile's rows out of shared memory.  A feature row crosses L2 -> SM |union|/|rows|
+ *   times instead of once per incident edge.  Rows with more distinct sources than max_union (the polar mesh
+ *   rows of the 512x256 grid->mesh graph, grid_mesh_connectivity.py:53-104) are listed as HEAVY and reduced by a
+ *   CTA-per-row kernel in a fixed order (no atomics).
+ *
+ * gcl_tile_plan_host builds the plan on the HOST from host copies of a CSR (rowptr/col of gcl_csr_build, either
+ *   orientation).  order: nullable permutation of the rows -- tiles take rows in this order, so an order with
+ *   spatial locality (the caller knows the mesh geometry) gives small unions; NULL = natural order.
+ *   Only rows < n_rows_out get a tile; entries whose column is >= n_rows_in are masked (zero rows).
+ *   pad_entries (1, 2 or 4): each row's entry list is padded to a multiple of it.
+ *   Output arrays are sized by the caller for the worst case: tile_rowptr/tile_uptr [n_rows+1], rows [n_rows],
+ *   eptr [n_rows+1], lidx/ek [nnz + (pad_entries-1)*n_rows], usrc [nnz], heavy_rows [n_rows], tile_desc [8*n_rows];
+ *   counts[8] = {n_tiles, n_plan_rows, n_union_total, n_entries, n_heavy, max_rows, max_union, max_entries}.
+ *   The caller uploads the used prefixes and fills a gcl_tile_plan with the DEVICE pointers.
+ */
+typedef struct gcl_tile_plan {
+  const int32_t* tile_rowptr;  /* [n_tiles+1] first plan row of each tile                                */
+  const int32_t* tile_uptr;    /* [n_tiles+1] first union entry of each tile                             */
+  const int32_t* rows;         /* [n_plan_rows] CSR row handled by plan row i                            */
+  const int32_t* eptr;         /* [n_plan_rows+1] first plan entry of plan row i                         */
+  const uint16_t* lidx;        /* [n_entries] index into the tile's union, 0xFFFF = masked               */
+  const int32_t* ek;           /* [n_entries] CSR position of the plan entry (weights / attention index) */
+  const int32_t* usrc;         /* [n_union_total] source rows of each tile's union                       */
+  const int32_t* heavy_rows;   /* [n_heavy] CSR rows outside the tiles (nullable if n_heavy == 0)        */
+  const int32_t* tile_desc;    /* [n_tiles][8] {first plan row, rows, first union entry, union size, first plan
+                                  entry, plan entries, 0, 0} -- what tile_rowptr/tile_uptr/eptr say, in one record */
+  int32_t n_tiles, n_heavy, max_rows, max_union, max_entries;
+  int32_t pad_entries;         /* every row's entry list is padded to a multiple of this (pad entries have
+                                  lidx = 0xFFFF, ek = -1); the pipelined SpMM kernel wants 2, the attention kernels 1 */
+} gcl_tile_plan;
+int gcl_tile_plan_host(const int32_t* rowptr, const int32_t* col, const int32_t* order, int64_t n_rows,
+                       int64_t n_rows_out, int64_t n_rows_in, int32_t max_rows, int32_t max_union,
+                       int32_t max_entries, int32_t pad_entries, int32_t* tile_rowptr, int32_t* tile_uptr,
+                       int32_t* rows, int32_t* eptr, uint16_t* lidx, int32_t* ek, int32_t* usrc,
+                       int32_t* heavy_rows, int32_t* tile_desc, int64_t* counts);
+/* plan: HOST pointer to a struct of DEVICE arrays, built with pad_entries = 2.  Persistent CTAs (one per SM) walk
+ * the (tile, sample block) items through a multi-stage shared-memory ring: the rows and the tile's index data of item
+ * i+2 are in flight (cp.async / cp.async.bulk) while item i is reduced.
+ * ent: int32 [n_entries][2] = {lidx, weight bits} in plan order (the caller gathers w[ek] once per weight kind);
+ *   pad and masked entries carry lidx = plan->max_union (the kernel's all-zero row), pads weight 0.  rowptr/col/w: the CSR the plan was built from, used for the heavy rows (w nullable = 1).
+ * channels: multiple of 4, <= 128, rows 16-byte aligned (otherwise GCL_ERR_BAD_ARG: use gcl_spmm_f32). */
+int gcl_spmm_tiled_f32(const gcl_tile_plan* plan, const int32_t* ent, const int32_t* rowptr, const int32_t* col,
+                       const float* w, const float* x, float* out, int64_t batch, int64_t n_rows_in,
+                       int64_t channels, int64_t x_bstride, int64_t out_bstride, const float* bias,
+                       const float* prelu_slope, float* z_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K7  node-wise dense transform  y = act(x W^T + b)  (torch.nn.Linear in MLP, models.py:74-98, and the
- *   bias-free `lin` inside GCNConv/GATConv).  x [R, Cin], W [Cout, Cin], y [R, Cout], fp32 FFMA with
- *   fp32 accumulation.  bias / prelu_slope / z_out nullable (z_out = value before PReLU).
- *   wt_scratch: device scratch of Cin*Cout floats (holds W^T).
+ *   bias-free `lin` inside GCNConv/GATConv).  x [R, Cin], W [Cout, Cin], y [R, Cout].  Default engine:
+ *   tcgen05 tensor cores in 3xTF32 (hi/lo operand split, fp32 accumulation in TMEM, TMA in and out) -- fp32-level
+ *   accuracy (rms error vs fp64 2.9e-7); rows < 2048 or widths that are not a multiple of 4 floats, and
+ *   gcl_set_dense_mode(GCL_DENSE_FFMA), take the fp32 FFMA kernels.
+ *   bias / prelu_slope / z_out nullable (z_out = value before PReLU).
+ *   wt_scratch: device scratch of Cin*Cout floats (holds the split / transposed W).
  */
 int gcl_linear_fwd_f32(const float* x, const float* W, const float* bias, float* y, int64_t rows,
                        int64_t c_in, int64_t c_out, const float* prelu_slope, float* z_out,
@@ -182,7 +235,10 @@ int gcl_layernorm_bwd_f32(const float* dy, const float* x, const float* gamma, c
  *   z [B, N, H, C] = lin(x);  a_s = <z, att_src>, a_d = <z, att_dst>   [B, N, H]
  *   e_ij = LeakyReLU_slope(a_s[j] + a_d[i]);  alpha = exp(e - max_i) / (sum_i exp(.) + 1e-16)
  *   out[b,i,:] = (concat ? [o_1..o_H] : mean_h o_h) + bias,  o_h = sum_j alpha_ijh z[b,j,h,:]
- * gcl_gat_fwd_f32 does logits + LeakyReLU + segment softmax + aggregation in ONE kernel.
+ * gcl_gat_fwd_f32: heads > 1 -- logits + LeakyReLU + segment softmax + aggregation + head mean/concat in ONE
+ *   kernel; heads == 1 -- a coefficient kernel (thread per (sample, receiver)) followed by the SpMM kernel with
+ *   per-sample weights (bias / PReLU in its epilogue): two launches, measured faster than the fused one
+ *   (DESIGN.md 3).  gcl_gat_fwd_tiled_f32 (below) is the single-kernel heads == 1 forward on a tile plan.
  *   alpha_csr  fp32 [B, nnz, H]  attention in CSR order (kept for backward)
  *   alpha_pyg  nullable fp32 [B, nnz, H] attention in PyG edge order (return_attention_weights=True)
  */
@@ -206,6 +262,22 @@ int gcl_gat_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* ro
                     const float* att_dst, const float* dout, float* g_csr, float* da_src,
                     float* da_dst, float* dz, int64_t batch, int64_t n_nodes, int64_t nnz,
                     int64_t heads, int64_t c, int concat, float negative_slope, void* stream);
+/* heads == 1 GATConv on tile plans (see gcl_tile_plan): ONE forward kernel -- the tile CTA stages the union's z rows
+ * by bulk copies, computes the attention coefficients of its rows (logits, LeakyReLU, segment softmax; written to
+ * alpha_csr [B, nnz] and optionally alpha_pyg) while the copies are in flight, then aggregates out of shared
+ * memory (+ bias, optional PReLU with z_out = pre-activation).  plan: receiver-grouped, no heavy rows. */
+int gcl_gat_fwd_tiled_f32(const gcl_tile_plan* plan, const int32_t* perm, const float* z, const float* a_src,
+                          const float* a_dst, const float* bias, float* out, float* alpha_csr, float* alpha_pyg,
+                          const float* prelu_slope, float* z_out, int64_t batch, int64_t n_nodes, int64_t nnz,
+                          int64_t c, float negative_slope, void* stream);
+/* heads == 1 backward on tile plans: pass 1 on the receiver-grouped plan (z rows of the union and the tile's dout
+ * rows in shared memory), pass 2 on the sender-grouped plan (dout rows of the union in shared memory).  Same
+ * outputs and per-row summation order as gcl_gat_bwd_f32. */
+int gcl_gat_bwd_tiled_f32(const gcl_tile_plan* plan, const gcl_tile_plan* plan_t, const int32_t* t2r, const float* z,
+                          const float* a_src, const float* a_dst, const float* alpha_csr, const float* att_src,
+                          const float* att_dst, const float* dout, float* g_csr, float* da_src, float* da_dst,
+                          float* dz, int64_t batch, int64_t n_nodes, int64_t nnz, int64_t c, float negative_slope,
+                          void* stream);
 /* datt_src[h,c] = sum_{b,n} da_src[b,n,h] z[b,n,h,c]  (same for dst).  Deterministic. */
 size_t gcl_gat_datt_workspace_bytes(int64_t rows, int64_t heads, int64_t c);
 int gcl_gat_datt_f32(const float* z, const float* da_src, const float* da_dst, float* datt_src,

@@ -294,12 +294,14 @@ def test_sparse_gat_prunes_and_reuses_graph():
         o2 = mine(X=X.to(DEV), attention_threshold=0.1, batch_num=5)
         c2 = ref(X=X, attention_threshold=0.1, batch_num=5)
         assert_close(o2, c2, 5e-4, "forward on the pruned graph")
+        g_after2 = mine.processing_graph
+        assert g_after2.shape[1] == ref.processing_graph.shape[1]     # pruned self loops are re-added (PyG)
         o3 = mine(X=X.to(DEV), attention_threshold=0.1, batch_num=6)
         assert torch.equal(o2, o3)
         # non-pruning calls leave the edge set alone, and the edge list they hand back is the cached CSR's own
         # PyG-order view, so the next call reuses that CSR instead of rebuilding it
         from gcl_b200.graph import CSR_LOOPS, GLOBAL_CACHE
-        assert mine.processing_graph.shape[1] == e1 == g_before.shape[1]
+        assert mine.processing_graph is g_after2 and g_before is not g_after2
         csr = GLOBAL_CACHE.get(mine.processing_graph, mine._num_mesh_nodes, CSR_LOOPS)
         assert mine.processing_graph is csr.edge_index_with_loops
 
