@@ -10,7 +10,7 @@ FLAGS=(-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompil
 pids=()
 for f in "$here"/*.cu; do
   o="$obj/$(basename "${f%.cu}").o"
-  if [[ ! -f "$o" || "$f" -nt "$o" || "$here/common.cuh" -nt "$o" || "$here/scan.cuh" -nt "$o" || "$here/tile.cuh" -nt "$o" || "$here/../../include/gcl_b200.h" -nt "$o" ]]; then
+  if [[ ! -f "$o" || "$f" -nt "$o" || "$here/common.cuh" -nt "$o" || "$here/scan.cuh" -nt "$o" || "$here/tile.cuh" -nt "$o" || "$here/ws.cuh" -nt "$o" || "$here/../../include/gcl_b200.h" -nt "$o" ]]; then
     "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" &
     pids+=($!)
   fi

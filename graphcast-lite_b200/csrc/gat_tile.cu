@@ -355,3 +355,186 @@ extern "C" int gcl_gat_bwd_tiled_f32(const gcl_tile_plan* plan, const gcl_tile_p
   }
   return GCL_OK;
 }
+
+// ================================================================================================================
+// Single-head GATConv on the persistent warp-specialised engine (ws.cuh).  The attention coefficients live in PLAN
+// order so that a tile's coefficients are one contiguous run the producers can copy:
+//   alpha_f [B, Ef]  receiver-grouped plan order      (forward aggregation, backward pass 1)
+//   alr_f   [B, Ef]  alpha * LeakyReLU'(logit)         (backward pass 1: g = alr (dalpha - t))
+//   alpha_t [B, Et]  sender-grouped plan order         (backward pass 2)
+//   g_t     [B, Et]  d(logit), written by pass 1 in sender-grouped plan order through f2t (plan entry -> plan entry)
+// Pads of the plans (rows are padded to entry pairs) hold 0 / must be zero-initialised by the caller (alpha_t, g_t).
+#include "ws.cuh"
+
+namespace gcl {
+namespace {
+
+// Attention coefficients in all three layouts.  8 lanes per (sample, plan row), lane j owns entry j of a chunk of 8
+// (every mesh row is one chunk): logits, segment softmax by group shuffles (PyG: exp(e - max) / (sum + 1e-16)),
+// coalesced plan-order stores.  pcol = plan-order sender ids (-1 for pads).
+__global__ void __launch_bounds__(256)
+    gat_alpha_plan_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ eptr,
+                          const int32_t* __restrict__ ek, const int32_t* __restrict__ pcol,
+                          const int32_t* __restrict__ perm, const int32_t* __restrict__ f2t,
+                          const float* __restrict__ a_src, const float* __restrict__ a_dst,
+                          float* __restrict__ alpha_f, float* __restrict__ alr_f, float* __restrict__ alpha_t,
+                          float* __restrict__ alpha_pyg, int n_plan_rows, int64_t N, int B, int64_t Ef, int64_t Et,
+                          int64_t nnz, float slope) {
+  const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+  if (t >= (int64_t)B * n_plan_rows) return;                   // whole 8-lane groups leave together
+  const int lane = threadIdx.x & 31, gl = lane & 7;
+  const unsigned mask = 0xffu << (lane & ~7);
+  const int i = (int)(t % n_plan_rows);
+  const int64_t b = t / n_plan_rows;
+  const int32_t row = __ldg(rows + i);
+  const int32_t e0 = __ldg(eptr + i), e1 = __ldg(eptr + i + 1);
+  const float adi = a_dst[b * N + row];
+  const float* as = a_src + b * N;
+  float* af = alpha_f + b * Ef;
+  float* ar = alr_f + b * Ef;
+  float* at = alpha_t + b * Et;
+  float* ap = alpha_pyg ? alpha_pyg + b * nnz : nullptr;
+  if (e1 - e0 <= 8) {                                          // one chunk: the lane keeps its entry in registers
+    const int32_t e = e0 + gl;
+    const int32_t c = e < e1 ? __ldg(pcol + e) : -1;
+    const float pre = c >= 0 ? as[c] + adi : 0.f;
+    const float lg = c >= 0 ? (pre > 0.f ? pre : slope * pre) : -INFINITY;
+    float m = lg;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(mask, m, o, 8));
+    const float ex = c >= 0 ? __expf(lg - m) : 0.f;
+    float l = ex;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) l += __shfl_xor_sync(mask, l, o, 8);
+    const float al = ex * (1.f / (l + 1e-16f));
+    if (e < e1) {
+      af[e] = al;
+      ar[e] = pre > 0.f ? al : al * slope;
+      if (c >= 0) {
+        at[__ldg(f2t + e)] = al;
+        if (ap) ap[__ldg(perm + __ldg(ek + e))] = al;
+      }
+    }
+    return;
+  }
+  float m = -INFINITY;
+  for (int32_t e = e0 + gl; e < e1; e += 8) {
+    const int32_t c = __ldg(pcol + e);
+    if (c >= 0) {
+      const float pre = as[c] + adi;
+      m = fmaxf(m, pre > 0.f ? pre : slope * pre);
+    }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(mask, m, o, 8));
+  float l = 0.f;
+  for (int32_t e = e0 + gl; e < e1; e += 8) {
+    const int32_t c = __ldg(pcol + e);
+    if (c >= 0) {
+      const float pre = as[c] + adi;
+      l += __expf((pre > 0.f ? pre : slope * pre) - m);
+    }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) l += __shfl_xor_sync(mask, l, o, 8);
+  const float rl = 1.f / (l + 1e-16f);
+  for (int32_t e = e0 + gl; e < e1; e += 8) {
+    const int32_t c = __ldg(pcol + e);
+    float al = 0.f, alr = 0.f;
+    if (c >= 0) {
+      const float pre = as[c] + adi;
+      al = __expf((pre > 0.f ? pre : slope * pre) - m) * rl;
+      alr = pre > 0.f ? al : al * slope;
+      at[__ldg(f2t + e)] = al;
+      if (ap) ap[__ldg(perm + __ldg(ek + e))] = al;
+    }
+    af[e] = al;
+    ar[e] = alr;
+  }
+}
+
+int check_ws_plan(const gcl_tile_plan* plan, const char* what) {
+  GCL_CHECK_ARG(plan && plan->n_tiles > 0 && plan->tile_desc && plan->rows && plan->eptr && plan->ek && plan->usrc,
+                "%s: missing plan arrays", what);
+  GCL_CHECK_ARG(plan->pad_entries == 2 || plan->pad_entries == 4, "%s: plans must be built with pad_entries = 2", what);
+  GCL_CHECK_ARG(plan->n_heavy == 0, "%s: plans with heavy rows are not supported; use gcl_gat_fwd_f32 / gcl_gat_bwd_f32", what);
+  return GCL_OK;
+}
+
+}  // namespace
+}  // namespace gcl
+
+extern "C" int gcl_gat_ws_supported(const gcl_tile_plan* plan, const gcl_tile_plan* plan_t, int64_t c, int64_t batch) {
+  if (!plan || !plan_t || plan->n_heavy || plan_t->n_heavy || plan->n_tiles <= 0 || plan_t->n_tiles <= 0) return 0;
+  if (plan->pad_entries < 2 || plan_t->pad_entries < 2 || c <= 0 || c % 4 || c > 128 || batch <= 0) return 0;
+  return ws_pick_sb(tile_args(plan), (int)c, (int)batch, 1) > 0 && ws_pick_sb(tile_args(plan), (int)c, (int)batch, 3) > 0 &&
+         ws_pick_sb(tile_args(plan_t), (int)c, (int)batch, 2) > 0;
+}
+
+extern "C" int gcl_gat_fwd_ws_f32(const gcl_tile_plan* plan, const int32_t* ent, const int32_t* pcol, const int32_t* perm,
+                                  const int32_t* f2t, const float* z, const float* a_src, const float* a_dst,
+                                  const float* bias, float* out, float* alpha_f, float* alr_f, float* alpha_t,
+                                  float* alpha_pyg, const float* prelu_slope, float* z_out, int64_t batch,
+                                  int64_t n_nodes, int64_t nnz, int64_t c, int64_t ef, int64_t et,
+                                  float negative_slope, void* stream) {
+  if (int rc = check_ws_plan(plan, "gcl_gat_fwd_ws_f32")) return rc;
+  GCL_CHECK_ARG(ent && pcol && f2t && z && a_src && a_dst && out && alpha_f && alr_f && alpha_t && z != out,
+                "gcl_gat_fwd_ws_f32: null pointer argument");
+  GCL_CHECK_ARG(!alpha_pyg || perm, "gcl_gat_fwd_ws_f32: alpha_pyg needs perm");
+  GCL_CHECK_ARG(c > 0 && c % 4 == 0 && c <= 128 && al16(z) && al16(out) && al16(ent) && (!bias || al16(bias)) &&
+                    (!z_out || al16(z_out)) && ef % 2 == 0 && et % 2 == 0 && al16(alpha_f),
+                "gcl_gat_fwd_ws_f32: needs 16-byte aligned rows of 4..128 channels and even plan entry counts");
+  GCL_CHECK_ARG(batch >= 0 && batch <= 65535 && n_nodes > 0 && n_nodes * c < (1ll << 31), "gcl_gat_fwd_ws_f32: bad sizes");
+  if (batch == 0) return GCL_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // the plan lists every row exactly once (no heavy rows): n_plan_rows == n_nodes
+  gat_alpha_plan_kernel<<<(unsigned)ceil_div(batch * n_nodes * 8, 256), 256, 0, s>>>(
+      plan->rows, plan->eptr, plan->ek, pcol, perm, f2t, a_src, a_dst, alpha_f, alr_f, alpha_t, alpha_pyg, (int)n_nodes,
+      n_nodes, (int)batch, ef, et, nnz, negative_slope);
+  GCL_CHECK_LAUNCH("gcl_gat_fwd_ws_f32(alpha)");
+  WsParams q{};
+  q.p = tile_args(plan);
+  q.ent = reinterpret_cast<const int2*>(ent);
+  q.x = z; q.x_bstride = n_nodes * c;
+  q.wa = alpha_f; q.w_bstride = ef;
+  q.out = out; q.out_bstride = n_nodes * c; q.z_out = z_out; q.bias = bias; q.prelu_slope = prelu_slope;
+  q.n_nodes = n_nodes; q.C = (int)c; q.B = (int)batch;
+  return ws_dispatch<1>(q, s, "gcl_gat_fwd_ws_f32");
+}
+
+extern "C" int gcl_gat_bwd_ws_f32(const gcl_tile_plan* plan, const int32_t* ent, const gcl_tile_plan* plan_t,
+                                  const int32_t* ent_t, const int32_t* f2t, const float* z, const float* alpha_f,
+                                  const float* alr_f, const float* alpha_t, const float* att_src, const float* att_dst,
+                                  const float* dout, float* g_t, float* da_src, float* da_dst, float* dz, int64_t batch,
+                                  int64_t n_nodes, int64_t c, int64_t ef, int64_t et, void* stream) {
+  if (int rc = check_ws_plan(plan, "gcl_gat_bwd_ws_f32")) return rc;
+  if (int rc = check_ws_plan(plan_t, "gcl_gat_bwd_ws_f32")) return rc;
+  GCL_CHECK_ARG(ent && ent_t && f2t && z && alpha_f && alr_f && alpha_t && att_src && att_dst && dout && g_t && da_src &&
+                    da_dst && dz,
+                "gcl_gat_bwd_ws_f32: null pointer argument");
+  GCL_CHECK_ARG(c > 0 && c % 4 == 0 && c <= 128 && al16(z) && al16(dout) && al16(dz) && al16(att_src) && al16(att_dst) &&
+                    al16(ent) && al16(ent_t) && ef % 2 == 0 && et % 2 == 0,
+                "gcl_gat_bwd_ws_f32: needs 16-byte aligned rows of 4..128 channels and even plan entry counts");
+  GCL_CHECK_ARG(batch >= 0 && batch <= 65535 && n_nodes > 0 && n_nodes * c < (1ll << 31), "gcl_gat_bwd_ws_f32: bad sizes");
+  if (batch == 0) return GCL_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    WsParams q{};
+    q.p = tile_args(plan);
+    q.ent = reinterpret_cast<const int2*>(ent);
+    q.x = z; q.x2 = dout; q.x_bstride = n_nodes * c;
+    q.wa = alpha_f; q.wb = alr_f; q.w_bstride = ef;
+    q.g_t = g_t; q.g_bstride = et; q.f2t = f2t; q.da_dst_out = da_dst;
+    q.n_nodes = n_nodes; q.C = (int)c; q.B = (int)batch;
+    if (int rc = ws_dispatch<3>(q, s, "gcl_gat_bwd_ws_f32(dst pass)")) return rc;
+  }
+  WsParams q{};
+  q.p = tile_args(plan_t);
+  q.ent = reinterpret_cast<const int2*>(ent_t);
+  q.x = dout; q.x_bstride = n_nodes * c;
+  q.wa = alpha_t; q.wb = g_t; q.w_bstride = et;
+  q.out = dz; q.out_bstride = n_nodes * c;
+  q.att_src = att_src; q.att_dst = att_dst; q.da_dst_in = da_dst; q.da_src_out = da_src;
+  q.n_nodes = n_nodes; q.C = (int)c; q.B = (int)batch;
+  return ws_dispatch<2>(q, s, "gcl_gat_bwd_ws_f32(src pass)");
+}

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "tile.cuh"
+#include "ws.cuh"
 
 namespace gcl {
 namespace {
@@ -171,296 +172,6 @@ __global__ void __launch_bounds__(kTileThreads)
   }
 }
 
-// ---- persistent, warp-specialised SpMM ----------------------------------------------------------------------
-// One CTA per SM walks items (sample block, tile) = blockIdx.x, + gridDim.x, ...  through a ring of kWsStages
-// shared-memory stages.  Stage = the union's rows of SB samples (+ one all-zero row that pad / masked entries
-// point to), the tile's packed entries {lidx, weight}, its row ids, entry offsets and descriptor.
-//   warps 0..3 (producers): wait for the stage to be released (mbarrier `empty`), issue the item's copies -- 16-byte
-//     cp.async chunks for the rows (source-row ids come from a small shared-memory buffer filled one item ahead),
-//     4/8/16-byte cp.async for the index data -- and lets the copies themselves signal `full`
-//     (cp.async.mbarrier.arrive.noinc): the producers never wait for data and run up to kWsStages items ahead.
-//   warps 4..19 (consumers): wait for `full`, reduce the tile's rows out of shared memory, release the stage.
-// The first tiled version (load -> sync -> compute inside one short-lived CTA) and a version in which all warps
-// both copied and computed were bound by the per-item latency chain (header -> source ids -> rows -> barrier), not
-// by HBM or by the gathers (ncu: barrier + scoreboard stalls, < 30% of DRAM peak).
-// The reduction is written for instruction count (ncu: 67 M warp instructions for 10 M FFMAs before): a lane owns
-// TWO 128-bit words of a row (a group of L = words/2 lanes per row), entries come as pairs from one LDS.128, pad
-// entries point at the zero row (no bounds test in the loop), and the products use the packed FFMA2
-// (fma.rn.f32x2, bit-identical to two fmaf).
-#ifndef GCL_WS_STAGES
-#define GCL_WS_STAGES 3
-#endif
-#ifndef GCL_WS_CW
-#define GCL_WS_CW 16
-#endif
-#ifndef GCL_WS_PW
-#define GCL_WS_PW 12
-#endif
-constexpr int kWsStages = GCL_WS_STAGES;
-constexpr int kWsConsumerWarps = GCL_WS_CW;
-constexpr int kWsProducerWarps = GCL_WS_PW;
-constexpr int kWsThreads = 32 * (kWsConsumerWarps + kWsProducerWarps);
-
-struct WsSmem {
-  int xs, ent, re, rid, desc, stage, us, bars, total;     // byte offsets (inside a stage / the CTA) and sizes
-};
-inline WsSmem ws_smem(const TileArgs& p, int C, int SB) {
-  WsSmem s;
-  int o = 0;
-  s.xs = o;   o += SB * (p.max_union + 1) * C * 4;
-  s.ent = o;  o += ((p.max_entries + 1) & ~1) * 8;
-  s.re = o;   o += ((p.max_rows + 1 + 3) & ~3) * 4;
-  s.rid = o;  o += ((p.max_rows + 3) & ~3) * 4;
-  s.desc = o; o += 32;
-  s.stage = (o + 127) & ~127;
-  s.us = kWsStages * s.stage;                              // source-row ids of the next two items
-  s.bars = s.us + 2 * ((p.max_union + 3) & ~3) * 4;
-  s.total = s.bars + 16 * kWsStages;
-  return s;
-}
-
-// acc.{x,y} += w * v.{x,y}; acc.{z,w} += w * v.{z,w}   (two FFMA2)
-__device__ __forceinline__ void fma4_packed(float4& acc, float w, const float4& v) {
-  unsigned long long a0, a1, v0, v1, ww;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w), "f"(w));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(acc.x), "f"(acc.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(acc.z), "f"(acc.w));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(v0) : "f"(v.x), "f"(v.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(v1) : "f"(v.z), "f"(v.w));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(v0), "l"(ww));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(v1), "l"(ww));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a0));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.z), "=f"(acc.w) : "l"(a1));
-}
-__device__ __forceinline__ void ws_cp16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void ws_cp4(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src) : "memory");
-}
-// the executing thread arrives on `bar` once all its earlier cp.async copies have landed (the arrival is part of
-// the barrier's expected count: .noinc)
-__device__ __forceinline__ void ws_cp_arrive(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
-}
-// consumer-side wait: back off between polls so that the spinning warps do not take issue slots from the producers
-__device__ __forceinline__ void ws_wait_backoff(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  while (!done) {
-#ifdef GCL_WS_SLEEP
-    __nanosleep(GCL_WS_SLEEP);
-#endif
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  }
-}
-__device__ __forceinline__ void ws_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-
-// LC = lanes that cover a row in 16-byte chunks (copy mapping); the reduction uses L = LC/2 lanes per row, each
-// owning words gl and gl + L (LC = 4: one word per lane)
-template <int LC, int SB>
-__global__ void __launch_bounds__(kWsThreads, 1)
-    spmm_ws_kernel(TileArgs p, WsSmem sm, const int2* __restrict__ ent, const float* __restrict__ x,
-                   float* __restrict__ out, int C, int64_t x_bstride, int64_t out_bstride, int B, int n_items,
-                   const float* __restrict__ bias, const float* __restrict__ prelu_slope, float* __restrict__ z_out,
-                   int dbg) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int words = C >> 2;
-  const int T = p.n_tiles;
-  const int zrow = p.max_union;                    // index of the all-zero row of a stage
-  const int n_my = blockIdx.x < n_items ? (n_items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-  const uint32_t rowb = (uint32_t)C * 4u;
-  const uint32_t sstride = (uint32_t)(zrow + 1) * rowb;
-  const uint32_t smem_base = tile_smem_u32(smem);
-  const uint32_t full0 = smem_base + sm.bars, empty0 = full0 + 8 * kWsStages;
-
-  for (int idx = tid; idx < kWsStages * SB * words; idx += kWsThreads) {      // the all-zero rows
-    const int st = idx / (SB * words), r = idx - st * SB * words, s = r / words, wd = r - s * words;
-    *reinterpret_cast<float4*>(smem + st * sm.stage + sm.xs + (uint32_t)s * sstride + (uint32_t)zrow * rowb + wd * 16) =
-        make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  if (tid == 0) {
-    for (int st = 0; st < kWsStages; ++st) {
-      tile_mbar_init(full0 + 8 * st, 32 * kWsProducerWarps); // every producer lane's copies arrive
-      tile_mbar_init(empty0 + 8 * st, kWsConsumerWarps);     // one arrival per consumer warp
-    }
-  }
-  __syncthreads();
-
-  if (warp < kWsProducerWarps) {
-    // ------------------------------------------------------------------------------------------- producers
-    // kWsProducerWarps warps share an item: copy group g = ptid / LC takes rows g, g + NG, ...; a warp requests
-    // exactly the source ids its own groups will use, so its private cp.async groups + __syncwarp order them.
-    constexpr int NG = 32 * kWsProducerWarps / LC;           // rows per pass of all producer threads
-    constexpr int RW = 32 / LC;                              // rows per warp-wide copy instruction
-    const int ptid = tid;                                    // producers are warps 0 .. kWsProducerWarps-1
-    const int part = lane & (LC - 1), g = ptid / LC;
-    const bool clive = part < words;
-    const int usz = ((zrow + 3) & ~3) * 4;                   // bytes of one source-id buffer
-    auto load_desc = [&](int j, int4& a, int4& b) {
-      if (j < n_my) {
-        const int4* dp = reinterpret_cast<const int4*>(p.tile_desc) + 2 * ((blockIdx.x + j * (int)gridDim.x) % T);
-        a = __ldg(dp);                                       // {r0, nr, u0, nu}
-        b = __ldg(dp + 1);                                   // {e0, ne, 0, 0}
-      } else {
-        a = b = make_int4(0, 0, 0, 0);
-      }
-    };
-    auto request_usrc = [&](int j, const int4& a) {          // this warp's source-row ids of item j -> us[j & 1]
-      for (int q = lane; ; q += 32) {
-        const int u = (q / RW) * NG + warp * RW + (q % RW);
-        if (u >= a.w) break;
-        ws_cp4(smem_base + sm.us + (j & 1) * usz + 4 * u, p.usrc + a.z + u);
-      }
-      cp_async_commit();
-    };
-    int4 da, db, na, nbq, fa, fb;                            // descriptors of items j, j+1, j+2
-    load_desc(0, da, db);
-    load_desc(1, na, nbq);
-    request_usrc(0, da);
-    for (int j = 0; j < n_my; ++j) {
-      const int slot = j % kWsStages;
-      request_usrc(j + 1, na);                               // commit order: ids(j+1) before rows(j)
-      load_desc(j + 2, fa, fb);                              // lands while this item's copies are issued
-      const int item = blockIdx.x + j * gridDim.x;
-      const int b0 = (item / T) * SB;
-      const int nb = min(SB, B - b0);
-      tile_mbar_wait(empty0 + 8 * slot, (uint32_t)(((j / kWsStages) & 1) ^ 1));   // consumers released the stage
-      if (j == 0) cp_async_wait<1>();              // ids(j) landed (ids(j+1) and rows(j-1) may still be in flight)
-      else cp_async_wait<2>();
-      __syncwarp();
-      const uint32_t st = smem_base + (uint32_t)slot * (uint32_t)sm.stage;
-      const int32_t* us = reinterpret_cast<const int32_t*>(smem + sm.us + (j & 1) * usz);
-      if (clive && !(dbg & 1)) {
-        // per-sample source pointers once per item; a row then costs one 32-bit multiply and, per sample, one
-        // 64-bit add and the copy (n_nodes * C < 2^31 is checked by the host)
-        const float* xp[SB];
-#pragma unroll
-        for (int s = 0; s < SB; ++s) xp[s] = x + (int64_t)(b0 + min(s, nb - 1)) * x_bstride + part * 4;
-        const uint32_t dst0 = st + sm.xs + part * 16;
-        if (nb == SB) {
-#pragma unroll 4
-          for (int u = g; u < da.w; u += NG) {
-            const uint32_t off = (uint32_t)us[u] * (uint32_t)C;
-            const uint32_t dst = dst0 + (uint32_t)u * rowb;
-#pragma unroll
-            for (int s = 0; s < SB; ++s) ws_cp16(dst + s * sstride, xp[s] + off);
-          }
-        } else {
-          for (int u = g; u < da.w; u += NG) {
-            const uint32_t off = (uint32_t)us[u] * (uint32_t)C;
-            const uint32_t dst = dst0 + (uint32_t)u * rowb;
-#pragma unroll
-            for (int s = 0; s < SB; ++s)
-              if (s < nb) ws_cp16(dst + s * sstride, xp[s] + off);
-          }
-        }
-      }
-      for (int i = ptid; i <= da.y; i += 32 * kWsProducerWarps) {
-        ws_cp4(st + sm.re + 4 * i, p.eptr + da.x + i);
-        if (i < da.y) ws_cp4(st + sm.rid + 4 * i, p.rows + da.x + i);
-      }
-      for (int e = 2 * ptid; e < db.y; e += 64 * kWsProducerWarps) ws_cp16(st + sm.ent + 8 * e, ent + db.x + e);
-      if (ptid < 2)
-        ws_cp16(st + sm.desc + 16 * ptid,
-                reinterpret_cast<const int4*>(p.tile_desc) + 2 * ((blockIdx.x + j * (int)gridDim.x) % T) + ptid);
-      ws_cp_arrive(full0 + 8 * slot);
-      cp_async_commit();
-      da = na; db = nbq; na = fa; nbq = fb;
-    }
-    cp_async_wait<0>();
-    return;
-  }
-
-  // --------------------------------------------------------------------------------------------- consumers
-  constexpr int L = LC >= 8 ? LC / 2 : LC;
-  constexpr int WPL = LC >= 8 ? 2 : 1;
-  constexpr int kGroups = kWsConsumerWarps * 32 / L;
-  const int ctid = tid - 32 * kWsProducerWarps;
-  const int gl = ctid & (L - 1), grp = ctid / L;
-  const bool live0 = gl < words, live1 = WPL == 2 && gl + L < words;
-  const uint32_t woff0 = live0 ? gl * 16 : 0, woff1 = live1 ? (gl + L) * 16 : 0;
-  float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f), bv1 = bv0;
-  if (bias && live0) bv0 = ldg4(bias + gl * 4);
-  if (bias && live1) bv1 = ldg4(bias + (gl + L) * 4);
-  const float slope = prelu_slope ? __ldg(prelu_slope) : 0.f;
-
-  for (int i = 0; i < n_my; ++i) {
-    const int slot = i % kWsStages;
-    const int item = blockIdx.x + i * gridDim.x;
-    const int b0 = (item / T) * SB;
-    const int nb = min(SB, B - b0);
-    ws_wait_backoff(full0 + 8 * slot, (uint32_t)((i / kWsStages) & 1));
-    const unsigned char* st = smem + slot * sm.stage;
-    const int nr = *reinterpret_cast<const int*>(st + sm.desc + 4);
-    const int e0 = *reinterpret_cast<const int*>(st + sm.desc + 16);
-    const int32_t* re = reinterpret_cast<const int32_t*>(st + sm.re);
-    const int32_t* rid = reinterpret_cast<const int32_t*>(st + sm.rid);
-    const int2* en = reinterpret_cast<const int2*>(st + sm.ent);
-    const unsigned char* xb[SB];     // ragged last sample block: sample nb-1 stands in (its result is not stored)
-#pragma unroll
-    for (int s = 0; s < SB; ++s) xb[s] = st + sm.xs + (uint32_t)min(s, nb - 1) * sstride;
-    for (int r = grp; r < ((dbg & 2) ? 0 : nr); r += kGroups) {
-      const int le0 = re[r] - e0, le1 = re[r + 1] - e0;               // even count: rows are padded to pairs
-      float4 acc0[SB], acc1[SB];
-#pragma unroll
-      for (int s = 0; s < SB; ++s) acc0[s] = acc1[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll(SB * WPL >= 4 ? 1 : 2)
-      for (int le = le0; le < le1; le += 2) {
-        const int4 e2 = *reinterpret_cast<const int4*>(en + le);      // two entries {lidx (pads: zero row), w}
-        const uint32_t o0 = (uint32_t)e2.x * rowb, o1 = (uint32_t)e2.z * rowb;
-        const float w0 = __int_as_float(e2.y), w1 = __int_as_float(e2.w);
-#pragma unroll
-        for (int s = 0; s < SB; ++s) {
-          const float4 va = *reinterpret_cast<const float4*>(xb[s] + o0 + woff0);
-          const float4 vb = *reinterpret_cast<const float4*>(xb[s] + o1 + woff0);
-          fma4_packed(acc0[s], w0, va);
-          fma4_packed(acc0[s], w1, vb);
-          if (WPL == 2) {
-            const float4 vc = *reinterpret_cast<const float4*>(xb[s] + o0 + woff1);
-            const float4 vd = *reinterpret_cast<const float4*>(xb[s] + o1 + woff1);
-            fma4_packed(acc1[s], w0, vc);
-            fma4_packed(acc1[s], w1, vd);
-          }
-        }
-      }
-      const int64_t row = rid[r];
-#pragma unroll
-      for (int s = 0; s < SB; ++s) {
-        if (s >= nb) break;
-        const int64_t o = (int64_t)(b0 + s) * out_bstride + row * C;
-        if (live0) {
-          float4 a = make_float4(acc0[s].x + bv0.x, acc0[s].y + bv0.y, acc0[s].z + bv0.z, acc0[s].w + bv0.w);
-          if (z_out) st4(z_out + o + gl * 4, a);
-          if (prelu_slope)
-            a = make_float4(prelu_f(a.x, slope), prelu_f(a.y, slope), prelu_f(a.z, slope), prelu_f(a.w, slope));
-          st4(out + o + gl * 4, a);
-        }
-        if (live1) {
-          float4 a = make_float4(acc1[s].x + bv1.x, acc1[s].y + bv1.y, acc1[s].z + bv1.z, acc1[s].w + bv1.w);
-          if (z_out) st4(z_out + o + (gl + L) * 4, a);
-          if (prelu_slope)
-            a = make_float4(prelu_f(a.x, slope), prelu_f(a.y, slope), prelu_f(a.z, slope), prelu_f(a.w, slope));
-          st4(out + o + (gl + L) * 4, a);
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) ws_arrive(empty0 + 8 * slot);                     // this warp is done with the stage
-  }
-}
-
 // Rows with more entries than a tile may hold: one CTA per (row, sample); warp w takes entries beg + w, beg + w + 8,
 // ... (a fixed assignment), the 8 partial rows are summed in warp order -> deterministic, no atomics.
 __global__ void __launch_bounds__(256)
@@ -573,53 +284,6 @@ int tile_dispatch(const gcl_tile_plan* plan, const TileCall& c, cudaStream_t s, 
   if (words <= 8) return tile_dispatch_sb<8, MODE>(sb, plan, c, s, what);
   if (words <= 16) return tile_dispatch_sb<16, MODE>(sb, plan, c, s, what);
   return tile_dispatch_sb<32, MODE>(sb, plan, c, s, what);
-}
-
-template <int LC, int SB>
-int ws_launch(const gcl_tile_plan* plan, const int2* ent, const float* x, float* out, int C, int64_t xbs, int64_t obs,
-              int B, const float* bias, const float* slope, float* z_out, cudaStream_t s) {
-  const TileArgs p = tile_args(plan);
-  const WsSmem sm = ws_smem(p, C, SB);
-  auto kern = spmm_ws_kernel<LC, SB>;
-  static bool attr_set = false;               // per instantiation
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return fail_cuda(e, "gcl_spmm_tiled_f32");
-    attr_set = true;
-  }
-  const int64_t n_items = (int64_t)plan->n_tiles * ceil_div(B, SB);
-  static const int ctas = getenv("GCL_TILE_CTAS") ? atoi(getenv("GCL_TILE_CTAS")) : kNumSMs;
-  const unsigned grid = (unsigned)std::min<int64_t>(n_items, ctas);
-  static const int dbg = getenv("GCL_TILE_DBG") ? atoi(getenv("GCL_TILE_DBG")) : 0;   // elimination runs (wrong results)
-  kern<<<grid, kWsThreads, sm.total, s>>>(p, sm, ent, x, out, C, xbs, obs, B, (int)n_items, bias, slope, z_out, dbg);
-  GCL_CHECK_LAUNCH("gcl_spmm_tiled_f32");
-  return GCL_OK;
-}
-
-template <int LC>
-int ws_dispatch_l(const gcl_tile_plan* plan, const int2* ent, const float* x, float* out, int C, int64_t xbs,
-                  int64_t obs, int B, const float* bias, const float* slope, float* z_out, cudaStream_t s) {
-  const TileArgs p = tile_args(plan);
-  static const int sb_cap = getenv("GCL_TILE_SB") ? atoi(getenv("GCL_TILE_SB")) : 4;
-  int sb = sb_cap;
-  while (sb > 1 && (sb > B || ws_smem(p, C, sb).total > 227 * 1024)) sb >>= 1;
-  if (ws_smem(p, C, sb).total > 227 * 1024) {
-    set_error("gcl_spmm_tiled_f32: a tile (union %d rows of %d channels) does not fit the shared-memory ring",
-              p.max_union, C);
-    return GCL_ERR_UNSUPPORTED;
-  }
-  if (sb == 4) return ws_launch<LC, 4>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
-  if (sb == 2) return ws_launch<LC, 2>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
-  return ws_launch<LC, 1>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
-}
-
-int pipe_dispatch(const gcl_tile_plan* plan, const int2* ent, const float* x, float* out, int C, int64_t xbs,
-                  int64_t obs, int B, const float* bias, const float* slope, float* z_out, cudaStream_t s) {
-  const int words = C / 4;
-  if (words <= 4) return ws_dispatch_l<4>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
-  if (words <= 8) return ws_dispatch_l<8>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
-  if (words <= 16) return ws_dispatch_l<16>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
-  return ws_dispatch_l<32>(plan, ent, x, out, C, xbs, obs, B, bias, slope, z_out, s);
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -743,9 +407,13 @@ extern "C" int gcl_spmm_tiled_f32(const gcl_tile_plan* plan, const int32_t* ent,
   if (batch == 0) return GCL_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (plan->n_tiles > 0) {
-    if (int rc = pipe_dispatch(plan, reinterpret_cast<const int2*>(ent), x, out, (int)channels, x_bstride, out_bstride,
-                               (int)batch, bias, prelu_slope, z_out, s))
-      return rc;
+    WsParams q{};
+    q.p = tile_args(plan);
+    q.ent = reinterpret_cast<const int2*>(ent);
+    q.x = x; q.x_bstride = x_bstride;
+    q.out = out; q.out_bstride = out_bstride; q.z_out = z_out; q.bias = bias; q.prelu_slope = prelu_slope;
+    q.C = (int)channels; q.B = (int)batch;
+    if (int rc = ws_dispatch<0>(q, s, "gcl_spmm_tiled_f32")) return rc;
   }
   if (plan->n_heavy > 0) {
     GCL_CHECK_ARG(plan->heavy_rows, "gcl_spmm_tiled_f32: plan lists heavy rows but has no heavy_rows array");

@@ -25,6 +25,9 @@ _PROTOS = {
     "gcl_spmm_tiled_f32": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, I64, P, P, P, P]),
     "gcl_gat_fwd_tiled_f32": (c_int, [P] * 11 + [I64, I64, I64, I64, F32, P]),
     "gcl_gat_bwd_tiled_f32": (c_int, [P] * 14 + [I64, I64, I64, I64, F32, P]),
+    "gcl_gat_ws_supported": (c_int, [P, P, I64, I64]),
+    "gcl_gat_fwd_ws_f32": (c_int, [P] * 16 + [I64, I64, I64, I64, I64, I64, F32, P]),
+    "gcl_gat_bwd_ws_f32": (c_int, [P] * 16 + [I64, I64, I64, I64, I64, P]),
     "gcl_linear_fwd_f32": (c_int, [P, P, P, P, I64, I64, I64, P, P, P, P]),
     "gcl_linear_fwd_scores_f32": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, P, P]),
     "gcl_linear_bwd_dx_f32": (c_int, [P, P, P, I64, I64, I64, P, P]),

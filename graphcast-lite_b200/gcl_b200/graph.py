@@ -157,6 +157,29 @@ class CSRGraph:
         self._weights = {}
         self._ei_view = None
         self._plans = {}
+        self._gat_ws = None
+
+    def gat_ws(self):
+        """What the warp-specialised single-head GAT kernels need besides the two plans (pad = 2): the packed entries
+        of both plans and f2t, the sender-grouped plan entry of every receiver-grouped plan entry (-1 for pads).
+        None if a plan has heavy rows."""
+        if self._gat_ws is None:
+            pf, pt = self.plan(False, pad=2), self.plan(True, pad=2)
+            if pf.n_heavy or pt.n_heavy or pf.n_tiles == 0:
+                self._gat_ws = False
+            else:
+                dev, nnz = self.rowptr.device, self.nnz
+                ek_f, ek_t = pf.t["ek"].long(), pt.t["ek"].long()
+                r2t = torch.empty(nnz, dtype=torch.long, device=dev)          # CSR position -> sender-grouped position
+                r2t[self.t2r[:nnz].long()] = torch.arange(nnz, device=dev)
+                real_t = ek_t >= 0
+                inv_t = torch.empty(nnz, dtype=torch.long, device=dev)        # sender-grouped position -> plan_t entry
+                inv_t[ek_t[real_t]] = torch.nonzero(real_t).squeeze(1)
+                f2t = torch.where(ek_f >= 0, inv_t[r2t[ek_f.clamp_min(0)]], torch.full_like(ek_f, -1)).to(torch.int32)
+                pcol = torch.where(ek_f >= 0, self.col.long()[ek_f.clamp_min(0)], torch.full_like(ek_f, -1))
+                self._gat_ws = (pf, pt, pf.entries(None, "unit"), pt.entries(None, "unit"), f2t.contiguous(),
+                                pcol.to(torch.int32).contiguous())
+        return self._gat_ws or None
 
     def plan(self, transposed: bool = False, n_rows_out: Optional[int] = None,
              n_rows_in: Optional[int] = None, pad: int = 2) -> TilePlan:

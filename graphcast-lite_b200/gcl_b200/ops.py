@@ -475,7 +475,7 @@ class _GAT(torch.autograd.Function):
         nnz = graph.nnz
         cout = HC if concat else C
         out = torch.empty((B, N, cout), dtype=torch.float32, device=dev)
-        alpha = torch.empty((B, max(nnz, 1), H), dtype=torch.float32, device=dev)
+        alpha = None
         alpha_pyg = torch.empty((B, max(nnz, 1), H), dtype=torch.float32, device=dev) if want_alpha else None
         zpre = torch.empty_like(out) if ps is not None else None
         with torch.cuda.device(dev):
@@ -484,19 +484,40 @@ class _GAT(torch.autograd.Function):
                       nbytes=4 * B * N * (H * C + 2 * H), tag=f"R{B * N}xH{H}xC{C}")
             nbytes = (4 * B * (N * (H * C + cout + 2 * H) + nnz * H * (2 if want_alpha else 1)) + 4 * nnz
                       + 4 * (N + 1))
-            plan = None
+            ws = None
             if H == 1 and nnz > 0 and _tileable(C, z3, out, bias_c, zpre):
-                plan = graph.plan(False, pad=1)
-                if plan.n_heavy:
-                    plan = None
-            if plan is not None:        # one kernel: coefficients + aggregation out of shared memory
-                _call("gcl_gat_fwd_tiled_f32", plan.ref, _p(graph.perm), _p(z3), _p(asrc), _p(adst), _p(bias_c),
-                      _p(out), _p(alpha), _p(alpha_pyg), _p(ps), _p(zpre), B, N, nnz, C, float(slope), _stream(),
-                      nbytes=nbytes, tag=f"N{N}xH{H}xC{C}xB{B}")
+                ws = graph.gat_ws()
+                if ws is not None and not _cabi.load().gcl_gat_ws_supported(ws[0].ref, ws[1].ref, C, B):
+                    ws = None
+            if ws is not None:          # coefficients in plan order + aggregation on the persistent tiled engine
+                pf, pt, ent_f, ent_t, f2t, pcol = ws
+                alpha = torch.empty((B, pf.n_entries), dtype=torch.float32, device=dev)       # alpha_f
+                alr = torch.empty((B, pf.n_entries), dtype=torch.float32, device=dev)
+                alpha_t = torch.zeros((B, pt.n_entries), dtype=torch.float32, device=dev)
+                _call("gcl_gat_fwd_ws_f32", pf.ref, _p(ent_f), _p(pcol), _p(graph.perm), _p(f2t), _p(z3), _p(asrc),
+                      _p(adst), _p(bias_c), _p(out), _p(alpha), _p(alr), _p(alpha_t), _p(alpha_pyg), _p(ps), _p(zpre),
+                      B, N, nnz, C, pf.n_entries, pt.n_entries, float(slope), _stream(), nbytes=nbytes,
+                      tag=f"N{N}xH{H}xC{C}xB{B}")
+                asrc, adst = alr, alpha_t            # what the backward needs in place of the node scores
+                mode = "ws"
             else:
-                _call("gcl_gat_fwd_f32", _p(graph.rowptr), _p(graph.col), _p(graph.perm), _p(z3), _p(asrc), _p(adst),
-                      _p(bias_c), _p(out), _p(alpha), _p(alpha_pyg), _p(ps), _p(zpre), B, N, nnz, H, C,
-                      int(bool(concat)), float(slope), _stream(), nbytes=nbytes, tag=f"N{N}xH{H}xC{C}xB{B}")
+                alpha = torch.empty((B, max(nnz, 1), H), dtype=torch.float32, device=dev)
+                plan = None
+                if H == 1 and nnz > 0 and _tileable(C, z3, out, bias_c, zpre):
+                    plan = graph.plan(False, pad=1)        # ring too small (wide rows): one-tile-per-CTA kernels
+                    if plan.n_heavy or graph.plan(True, pad=1).n_heavy:
+                        plan = None
+                if plan is not None:
+                    _call("gcl_gat_fwd_tiled_f32", plan.ref, _p(graph.perm), _p(z3), _p(asrc), _p(adst), _p(bias_c),
+                          _p(out), _p(alpha), _p(alpha_pyg), _p(ps), _p(zpre), B, N, nnz, C, float(slope), _stream(),
+                          nbytes=nbytes, tag=f"N{N}xH{H}xC{C}xB{B}")
+                    mode = "tiled"
+                else:
+                    _call("gcl_gat_fwd_f32", _p(graph.rowptr), _p(graph.col), _p(graph.perm), _p(z3), _p(asrc),
+                          _p(adst), _p(bias_c), _p(out), _p(alpha), _p(alpha_pyg), _p(ps), _p(zpre), B, N, nnz, H, C,
+                          int(bool(concat)), float(slope), _stream(), nbytes=nbytes, tag=f"N{N}xH{H}xC{C}xB{B}")
+                    mode = "rows"
+        ctx.ws, ctx.mode = mode == "ws", mode
         ctx.graph, ctx.H, ctx.C, ctx.concat, ctx.slope = graph, H, C, bool(concat), float(slope)
         ctx.squeeze, ctx.has_bias, ctx.has_prelu = squeeze, bias is not None, ps is not None
         ctx.save_for_backward(z3, asrc, adst, alpha, a_s, a_d, zpre, ps)
@@ -520,9 +541,9 @@ class _GAT(torch.autograd.Function):
             d3, dslope = prelu_bwd_raw(d3, zpre, ps)
             dslope = dslope.view_as(ps)
         dev = z3.device
-        gbuf = torch.empty_like(alpha)
-        da_s = torch.empty_like(asrc)
-        da_d = torch.empty_like(adst)
+        gbuf = torch.empty_like(alpha) if not ctx.ws else None
+        da_s = torch.empty_like(asrc) if not ctx.ws else None
+        da_d = torch.empty_like(adst) if not ctx.ws else None
         dz = torch.empty_like(z3)
         datt_s = torch.empty(HC, dtype=torch.float32, device=dev)
         datt_d = torch.empty(HC, dtype=torch.float32, device=dev)
@@ -531,15 +552,19 @@ class _GAT(torch.autograd.Function):
         ws = _ws(nb, dev)
         with torch.cuda.device(dev):
             nbytes = 4 * B * (N * (2 * H * C + d3.shape[-1] + 4 * H) + 3 * g.nnz * H) + 16 * g.nnz
-            plans = None
-            if H == 1 and g.nnz > 0 and _tileable(C, z3, d3, dz, a_s, a_d):
-                plans = (g.plan(False, pad=1), g.plan(True, pad=1))
-                if plans[0].n_heavy or plans[1].n_heavy:
-                    plans = None
-            if plans is not None:
-                _call("gcl_gat_bwd_tiled_f32", plans[0].ref, plans[1].ref, _p(g.t2r), _p(z3), _p(asrc), _p(adst),
-                      _p(alpha), _p(a_s), _p(a_d), _p(d3), _p(gbuf), _p(da_s), _p(da_d), _p(dz), B, N, g.nnz, C,
-                      ctx.slope, _stream(), nbytes=nbytes, tag=f"N{N}xH{H}xC{C}xB{B}")
+            if ctx.ws:
+                pf, pt, ent_f, ent_t, f2t, _ = g.gat_ws()
+                alr, alpha_t = asrc, adst            # (saved in their place by the forward)
+                g_t = torch.zeros_like(alpha_t)
+                da_s = torch.empty((B, N, 1), dtype=torch.float32, device=dev)
+                da_d = torch.empty((B, N, 1), dtype=torch.float32, device=dev)
+                _call("gcl_gat_bwd_ws_f32", pf.ref, _p(ent_f), pt.ref, _p(ent_t), _p(f2t), _p(z3), _p(alpha), _p(alr),
+                      _p(alpha_t), _p(a_s), _p(a_d), _p(d3), _p(g_t), _p(da_s), _p(da_d), _p(dz), B, N, C,
+                      pf.n_entries, pt.n_entries, _stream(), nbytes=nbytes, tag=f"N{N}xH{H}xC{C}xB{B}")
+            elif ctx.mode == "tiled":
+                _call("gcl_gat_bwd_tiled_f32", g.plan(False, pad=1).ref, g.plan(True, pad=1).ref, _p(g.t2r), _p(z3),
+                      _p(asrc), _p(adst), _p(alpha), _p(a_s), _p(a_d), _p(d3), _p(gbuf), _p(da_s), _p(da_d), _p(dz),
+                      B, N, g.nnz, C, ctx.slope, _stream(), nbytes=nbytes, tag=f"N{N}xH{H}xC{C}xB{B}")
             else:
                 _call("gcl_gat_bwd_f32", _p(g.rowptr), _p(g.col), _p(g.rowptr_t), _p(g.col_t), _p(g.t2r), _p(z3),
                       _p(asrc), _p(adst), _p(alpha), _p(a_s), _p(a_d), _p(d3), _p(gbuf), _p(da_s), _p(da_d), _p(dz),

@@ -278,6 +278,30 @@ int gcl_gat_bwd_tiled_f32(const gcl_tile_plan* plan, const gcl_tile_plan* plan_t
                           const float* att_dst, const float* dout, float* g_csr, float* da_src, float* da_dst,
                           float* dz, int64_t batch, int64_t n_nodes, int64_t nnz, int64_t c, float negative_slope,
                           void* stream);
+/* heads == 1 GATConv on the persistent warp-specialised engine (the one behind gcl_spmm_tiled_f32).  The attention
+ * coefficients are kept in PLAN order, so a tile's coefficients are contiguous and travel with its rows:
+ *   alpha_f [B, ef] receiver-grouped plan order; alr_f [B, ef] = alpha * LeakyReLU'(logit);
+ *   alpha_t [B, et] sender-grouped plan order (ZERO-INITIALISED by the caller: plan pads are never written);
+ *   g_t     [B, et] d(logit) in sender-grouped plan order (scratch, ZERO-INITIALISED by the caller);
+ *   f2t int32 [ef]: sender-grouped plan entry of receiver-grouped plan entry e (-1 for pads);
+ *   pcol int32 [ef]: sender of receiver-grouped plan entry e (col[ek[e]], -1 for pads);
+ *   ent / ent_t: packed plan entries as for gcl_spmm_tiled_f32 (the weight field is ignored);
+ *   plan / plan_t: pad_entries = 2, no heavy rows, every node in exactly one tile.
+ * Forward = coefficient kernel (thread per (sample, row); writes alpha_f, alr_f, alpha_t and optionally alpha_pyg)
+ *   + aggregation with per-sample weights (+ bias, optional PReLU with z_out = pre-activation).
+ * Backward = pass 1 on the receiver-grouped plan (g_t, da_dst) + pass 2 on the sender-grouped plan (dz, da_src);
+ *   same outputs as gcl_gat_bwd_f32.  gcl_gat_ws_supported: 1 if the tiles fit the shared-memory ring. */
+int gcl_gat_ws_supported(const gcl_tile_plan* plan, const gcl_tile_plan* plan_t, int64_t c, int64_t batch);
+int gcl_gat_fwd_ws_f32(const gcl_tile_plan* plan, const int32_t* ent, const int32_t* pcol, const int32_t* perm,
+                       const int32_t* f2t, const float* z, const float* a_src, const float* a_dst, const float* bias,
+                       float* out, float* alpha_f, float* alr_f, float* alpha_t, float* alpha_pyg,
+                       const float* prelu_slope, float* z_out, int64_t batch, int64_t n_nodes, int64_t nnz, int64_t c,
+                       int64_t ef, int64_t et, float negative_slope, void* stream);
+int gcl_gat_bwd_ws_f32(const gcl_tile_plan* plan, const int32_t* ent, const gcl_tile_plan* plan_t, const int32_t* ent_t,
+                       const int32_t* f2t, const float* z, const float* alpha_f, const float* alr_f,
+                       const float* alpha_t, const float* att_src, const float* att_dst, const float* dout, float* g_t,
+                       float* da_src, float* da_dst, float* dz, int64_t batch, int64_t n_nodes, int64_t c, int64_t ef,
+                       int64_t et, void* stream);
 /* datt_src[h,c] = sum_{b,n} da_src[b,n,h] z[b,n,h,c]  (same for dst).  Deterministic. */
 size_t gcl_gat_datt_workspace_bytes(int64_t rows, int64_t heads, int64_t c);
 int gcl_gat_datt_f32(const float* z, const float* da_src, const float* da_dst, float* datt_src,

@@ -107,6 +107,7 @@ def main():
                 if mode == "tiled hint":
                     gg.ORDER_HINTS.update(hints)
                 g._plans.clear()
+                g._gat_ws = None
                 prof = ops.KernelProfiler()
                 with torch.no_grad():
                     us = timeit(lambda: ops.gat_attend(z, a_s, a_d, bia, g, 1, False, 0.2))
@@ -119,7 +120,7 @@ def main():
                     torch.autograd.grad(out, (z, a_s, a_d, bia), go, retain_graph=True)
                 ops.PROFILER = None
                 for (name, tag), a in prof.summary().items():
-                    if name.startswith("gcl_gat_bwd"):
+                    if name.startswith("gcl_gat_bwd") or name.startswith("gcl_gat_fwd"):
                         report(f"   {name} ({mode})", 1e3 * a["ms"] / a["calls"], nb_b)
             gg.TILED = True
             gg.ORDER_HINTS.update(hints)
