@@ -445,6 +445,71 @@ def bench_dropin_b1(name, args, dev, cpu_value=None):
     return res
 
 
+def bench_input_pipeline(name, args, dev):
+    """f2: a synthetic dataset in the reference's raw on-disk format (float16 memmap (T, lon, lat, F) + scalers.npz),
+    read through gcl_b200.data.ChunkedWindowLoader: host staging of raw windows -> H2D -> gcl_window_assemble; alone,
+    and feeding the captured training step (every batch comes from disk / page cache, none is re-sent)."""
+    import shutil
+    import numpy as np
+    import torch
+    from gcl_b200.data import ChunkedWindowLoader
+    from gcl_b200.model import WeatherPrediction
+    from gcl_b200.train import Trainer
+    from gcl_b200.workloads import get_workload
+    cfg = get_workload(name)
+    nlat, nlon = cfg["nlat"], cfg["nlon"]
+    F, T, P = cfg["data"]["num_features_used"], cfg["data"]["obs_window_used"], cfg["data"]["pred_window_used"]
+    B = DEFAULT_BATCH[name]
+    n_batches = 12
+    frames = B * n_batches + T + P - 1
+    tmp = tempfile.mkdtemp(prefix="gcl_bench_data_")
+    try:
+        rng = np.random.default_rng(0)
+        mm = np.memmap(os.path.join(tmp, "data.npy"), dtype=np.float16, mode="w+", shape=(frames, nlon, nlat, F))
+        block = rng.standard_normal((8, nlon, nlat, F), dtype=np.float32).astype(np.float16)
+        for t0 in range(0, frames, 8):
+            mm[t0:t0 + 8] = block[: min(8, frames - t0)]
+        mm.flush()
+        del mm
+        json.dump({"n_time": frames, "n_lon": nlon, "n_lat": nlat, "n_feat": F}, open(os.path.join(tmp, "dataset_info.json"), "w"))
+        np.savez(os.path.join(tmp, "scalers.npz"), mean=np.zeros(F, np.float32), std=np.ones(F, np.float32), n=np.int64(frames))
+        ld = ChunkedWindowLoader(tmp, T, P, "all", None, device=dev)
+        raw_bytes = B * (T + P) * nlon * nlat * F * 2
+        for _ in ld.batches(B, drop_last=True):       # warm the page cache and the kernel
+            pass
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        n = 0
+        for X, Y in ld.batches(B, drop_last=True):
+            n += X.shape[0]
+        torch.cuda.synchronize(dev)
+        loader_s = time.perf_counter() - t0
+        torch.manual_seed(42)
+        model = WeatherPrediction(cfg, nlat, nlon, dev)
+        tr = Trainer(model, nlat, nlon, lr=cfg["learning_rate"], ar_steps=1)
+        tr.capture(B, T * F, P * F)
+        for X, Y in ld.batches(B, drop_last=True):
+            tr.step_from_device(X, Y)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        m = 0
+        for X, Y in ld.batches(B, drop_last=True):
+            loss = tr.step_from_device(X, Y)
+            m += X.shape[0]
+        last = float(loss.item())
+        train_s = time.perf_counter() - t0
+        res = {"workload": name, "batch": B, "format": "raw float16 memmap (T, lon, lat, F), page cache",
+               "api": "ChunkedWindowLoader.batches() -> Trainer.step_from_device()",
+               "loader": {"value": n / loader_s, "unit": UNIT, "raw_GBps": raw_bytes * (n / B) / loader_s / 1e9},
+               "train_from_loader": {"value": m / train_s, "unit": UNIT, "ms_per_step": 1e3 * train_s / (m / B),
+                                     "h2d_bytes_per_step": raw_bytes, "loss": last}}
+        del tr, model
+        torch.cuda.empty_cache()
+        return res
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def bench_cpu_layers(seconds=3.0):
     """Per-layer mesh message passing on the host cores: the oracle's restated PyG GCNConv / GATConv on
     the [3,5] multi-mesh, 64 channels, batch 1, edges incl. self loops per second, forward and forward + backward."""
@@ -528,6 +593,7 @@ def run_gcl(args):
         out["workloads"] = wl
         cpu_att = next((w["cpu_baseline"]["value"] for w in wl if w["workload"] == "attention" and w["cpu_baseline"]), None)
         out["dropin_b1"] = bench_dropin_b1("attention", args, dev, cpu_att)
+        out["input_pipeline"] = bench_input_pipeline("attention", args, dev)
         if not args.no_cpu_baseline:
             out["cpu_layers"] = bench_cpu_layers()
     if rank == 0:

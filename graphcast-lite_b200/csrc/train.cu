@@ -61,6 +61,74 @@ __global__ void wmse_kernel(const float* __restrict__ delta, const float* __rest
   }
 }
 
+// One autoregressive training step behind the model (train.py:201-227), one pass over [B, G, C]:
+//   out = (residual ? state[.., obs-1, :] : 0) + delta;  loss part = sum w (out - y)^2, w = node_w[g] chan_w[c];
+//   g_loss = gscale w (out - y);  new_state = [state[.., 1:, :], out'] with out'[c] = static ? x_last : forcing ? y : out
+__global__ void ar_step_kernel(const float* __restrict__ delta, const float* __restrict__ state,
+                               const float* __restrict__ y, int64_t y_stride, const float* __restrict__ node_w,
+                               const float* __restrict__ chan_w, const int32_t* __restrict__ carry, int residual,
+                               float* __restrict__ new_state, float* __restrict__ g_loss, float* __restrict__ part,
+                               float gscale, int64_t G, int obs, int C, int64_t total, int64_t per_block) {
+  __shared__ float sm[kT / 32];
+  const int64_t beg = (int64_t)blockIdx.x * per_block, end = min(total, beg + per_block);
+  float s = 0.f;
+  for (int64_t idx = beg + threadIdx.x; idx < end; idx += kT) {
+    const int c = (int)(idx % C);
+    const int64_t bg = idx / C;
+    const int64_t g = bg % G;
+    const float* st = state + bg * (int64_t)obs * C + c;
+    const float xl = st[(int64_t)(obs - 1) * C];
+    const float yv = y ? y[bg * y_stride + c] : 0.f;
+    const float o = delta[idx] + (residual ? xl : 0.f);
+    const float diff = o - yv;
+    const float w = (node_w ? __ldg(node_w + g) : 1.f) * (chan_w ? __ldg(chan_w + c) : 1.f);
+    if (g_loss) g_loss[idx] = gscale * w * diff;
+    s = fmaf(w * diff, diff, s);
+    if (new_state) {
+      float* ns = new_state + bg * (int64_t)obs * C + c;
+      for (int t = 0; t + 1 < obs; ++t) ns[(int64_t)t * C] = st[(int64_t)(t + 1) * C];
+      const int cr = carry ? __ldg(carry + c) : 0;
+      ns[(int64_t)(obs - 1) * C] = cr == 1 ? xl : (cr == 2 ? yv : o);
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kT / 32; ++k) t += sm[k];
+    part[blockIdx.x] = t;
+  }
+}
+
+// backward of ar_step: d_delta = g_loss dloss + (carry == 0) d_new[obs-1];
+//   d_state[t] = (t >= 1 ? d_new[t-1] : 0) + (t == obs-1 ? residual d_delta + (carry == 1) d_new[obs-1] : 0)
+__global__ void ar_step_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ dloss,
+                                   const float* __restrict__ d_new, const int32_t* __restrict__ carry, int residual,
+                                   float* __restrict__ d_delta, float* __restrict__ d_state, int obs, int C,
+                                   int64_t total) {
+  const float dl = dloss ? __ldg(dloss) : 1.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int c = (int)(idx % C);
+    const int64_t bg = idx / C;
+    const int cr = carry ? __ldg(carry + c) : 0;
+    const float* dn = d_new ? d_new + bg * (int64_t)obs * C + c : nullptr;
+    const float dlast = dn ? dn[(int64_t)(obs - 1) * C] : 0.f;
+    const float dd = g_loss[idx] * dl + (cr == 0 ? dlast : 0.f);
+    d_delta[idx] = dd;
+    if (d_state) {
+      float* ds = d_state + bg * (int64_t)obs * C + c;
+      for (int t = 0; t < obs; ++t) {
+        float v = (t >= 1 && dn) ? dn[(int64_t)(t - 1) * C] : 0.f;
+        if (t == obs - 1) v += (residual ? dd : 0.f) + (cr == 1 ? dlast : 0.f);
+        ds[(int64_t)t * C] = v;
+      }
+    }
+  }
+}
+
 __global__ void wmse_finish_kernel(const float* __restrict__ part, int n, float inv_wsum, float* __restrict__ loss,
                                    int accumulate) {
   float s = 0.f;
@@ -221,4 +289,42 @@ extern "C" int gcl_rows_split_f32(const float* x, float* a, float* b_, int64_t b
   const int rc = rows_cat<false>(a, b_, const_cast<float*>(x), batch, na, nb, c, stream);
   GCL_CHECK_LAUNCH("gcl_rows_split_f32");
   return rc;
+}
+
+extern "C" int gcl_ar_step_f32(const float* delta, const float* state, const float* y, int64_t y_stride,
+                               const float* node_w, const float* chan_w, const int32_t* carry, int residual,
+                               float inv_wsum, float scale, float* new_state, float* g_loss, float* loss_out,
+                               int accumulate, int64_t batch, int64_t n_grid, int64_t obs, int64_t c, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  GCL_CHECK_ARG(delta && state && loss_out && workspace, "gcl_ar_step_f32: null pointer argument");
+  GCL_CHECK_ARG(batch >= 0 && n_grid > 0 && c > 0 && obs > 0 && y_stride >= c, "gcl_ar_step_f32: bad sizes");
+  GCL_CHECK_ARG(new_state != state, "gcl_ar_step_f32: new_state must not alias state");
+  if (workspace_bytes < gcl_wmse_workspace_bytes(batch, n_grid, c)) {
+    set_error("gcl_ar_step_f32: workspace too small");
+    return GCL_ERR_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t total = batch * n_grid * c;
+  const int nblk = blocks_for(total);
+  const int64_t per_block = ceil_div(total, nblk);
+  float* part = static_cast<float*>(workspace);
+  ar_step_kernel<<<nblk, kT, 0, s>>>(delta, state, y, y_stride, node_w, chan_w, carry, residual, new_state, g_loss, part,
+                                     2.f * scale * inv_wsum, n_grid, (int)obs, (int)c, total, per_block);
+  GCL_CHECK_LAUNCH("gcl_ar_step_f32");
+  wmse_finish_kernel<<<1, 32, 0, s>>>(part, nblk, inv_wsum * scale, loss_out, accumulate);
+  GCL_CHECK_LAUNCH("gcl_ar_step_f32(finish)");
+  return GCL_OK;
+}
+
+extern "C" int gcl_ar_step_bwd_f32(const float* g_loss, const float* dloss, const float* d_new_state,
+                                   const int32_t* carry, int residual, float* d_delta, float* d_state, int64_t batch,
+                                   int64_t n_grid, int64_t obs, int64_t c, void* stream) {
+  GCL_CHECK_ARG(g_loss && d_delta, "gcl_ar_step_bwd_f32: null pointer argument");
+  GCL_CHECK_ARG(batch >= 0 && n_grid > 0 && c > 0 && obs > 0, "gcl_ar_step_bwd_f32: bad sizes");
+  const int64_t total = batch * n_grid * c;
+  if (total == 0) return GCL_OK;
+  ar_step_bwd_kernel<<<blocks_for(total), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+      g_loss, dloss, d_new_state, carry, residual, d_delta, d_state, (int)obs, (int)c, total);
+  GCL_CHECK_LAUNCH("gcl_ar_step_bwd_f32");
+  return GCL_OK;
 }

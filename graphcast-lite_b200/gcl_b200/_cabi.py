@@ -63,6 +63,11 @@ _PROTOS = {
     "gcl_rows_split_f32": (c_int, [P, P, P, I64, I64, I64, I64, P]),
     "gcl_wmse_workspace_bytes": (SZ, [I64, I64, I64]),
     "gcl_wmse_f32": (c_int, [P, P, I64, P, I64, P, F32, P, P, P, I32, F32, I64, I64, I64, P, SZ, P]),
+    "gcl_ar_step_f32": (c_int, [P, P, P, I64, P, P, P, I32, F32, F32, P, P, P, I32, I64, I64, I64, I64, P, SZ, P]),
+    "gcl_ar_step_bwd_f32": (c_int, [P, P, P, P, I32, P, P, I64, I64, I64, I64, P]),
+    "gcl_window_assemble": (c_int, [P, I32, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P]),
+    "gcl_forecast_metrics_workspace_bytes": (SZ, [I64, I64]),
+    "gcl_forecast_metrics_f32": (c_int, [P, P, P, I64, I64, I64, P, SZ, P]),
     "gcl_adam_f32": (c_int, [P, P, P, P, I64, F32, F32, F32, F32, F32, P, P]),
 }
 

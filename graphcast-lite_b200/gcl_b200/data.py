@@ -4,9 +4,10 @@ Mirrors TimeseriesChunkDataset of /root/reference/src/data/dataloader_chunked.py
 float16 memmap `data.npy` + `dataset_info.json`, or legacy `chunk_*.npy`; `scalers.npz`), same sliding-window sample
 index that never crosses a chunk boundary (:137-149), same time-ordered splits (:151-174) -- but moves the arithmetic
 off the host: the reference converts, normalises and transposes every window on CPU workers (:189-223); here the host
-only copies the raw float16 window into a pinned staging buffer (half the bytes, no math), and the float32 convert,
-(x - mean) / std, the (lat, lon)-major flatten and the obs / target split run on the device for the whole batch.
-Results are bit-identical to the reference's (same IEEE float32 operations in the same order).
+only copies the raw float16 window into a pinned staging buffer (half the bytes, no math), and ONE kernel
+(gcl_window_assemble) does the float32 convert, (x - mean) / std, the (lat, lon)-major flatten and the obs / target
+split on the device for the whole batch.  Results are bit-identical to the reference's (same IEEE float32 operations).
+The device side is CUDA only (no CPU fallback); `raw=True` returns the staged raw windows for host-side use.
 """
 import glob
 import json
@@ -16,6 +17,8 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
+
+from . import _cabi
 
 
 class ChunkedWindowLoader:
@@ -88,8 +91,13 @@ class ChunkedWindowLoader:
             ci, t = self.sample_indices[int(i)]
             host[b] = self.chunks[ci][t: t + window]
 
-    def batch(self, indices: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
-        """X [B, G, obs*F], Y [B, G, pred*F] float32 on self.device for the given sample indices."""
+    def batch(self, indices: Sequence[int], raw: bool = False):
+        """X [B, G, obs*F], Y [B, G, pred*F] float32 on self.device for the given sample indices.
+        raw=True: the staged raw windows [B, W, ...] (host tensor, stored dtype) instead -- no device involved."""
+        if raw:
+            t = torch.empty((len(indices), self.obs_window + self.pred_steps) + self.frame_shape, dtype=self.raw_dtype)
+            self._fill(t, indices)
+            return t
         if self._stage_free is not None:
             self._stage_free.synchronize()       # the previous batch()'s H2D copy may still be reading the buffer
         stage = self._staging(len(indices))
@@ -101,7 +109,7 @@ class ChunkedWindowLoader:
         return out
 
     def batches(self, batch_size: int, shuffle: bool = False, seed: int = 0, drop_last: bool = False,
-                rank: int = 0, world: int = 1):
+                rank: int = 0, world: int = 1, raw: bool = False):
         """Iterate over the split in batches (rank r of a data-parallel job takes samples r::world).  Every rank gets
         the same number of samples -- the order is wrap-padded to a multiple of `world` first, as
         torch.utils.data.DistributedSampler does -- so all ranks run the same number of (collective) steps.  The host
@@ -117,6 +125,10 @@ class ChunkedWindowLoader:
         if drop_last and groups and len(groups[-1]) < batch_size:
             groups.pop()
         if not groups:
+            return
+        if raw:                                    # host-side consumers (and the host-logic tests): staged raw windows
+            for g in groups:
+                yield self.batch(g, raw=True)
             return
         window = self.obs_window + self.pred_steps
         cuda = self.device.type == "cuda"
@@ -142,14 +154,22 @@ class ChunkedWindowLoader:
             yield out
 
     def _to_device(self, stage: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.device.type != "cuda":
+            raise RuntimeError("gcl_b200.data: the convert / normalise / transpose kernel is CUDA only; there is no CPU "
+                               "fallback (use raw=True for the staged raw windows)")
         B, window = stage.shape[0], self.obs_window + self.pred_steps
         raw = stage.to(self.device, non_blocking=True)
-        w = (raw[..., : self.n_feat].float() - self.mean) / self.std     # dataloader_chunked.py:190-191 / 204-207
-        if self.flat_grid:                                               # [B, W, N, F] -> [B, N, W, F]        (:196-199)
-            w = w.permute(0, 2, 1, 3)
-        else:                                                            # [B, W, lon, lat, F] -> [B, lat, lon, W, F] (:218-221)
-            w = w.permute(0, 3, 2, 1, 4)
-        w = w.reshape(B, self.grid_nodes, window, self.n_feat)
-        X = w[:, :, : self.obs_window].reshape(B, self.grid_nodes, self.obs_window * self.n_feat)
-        Y = w[:, :, self.obs_window:].reshape(B, self.grid_nodes, self.pred_steps * self.n_feat)
-        return X.contiguous(), Y.contiguous()
+        code = {torch.float16: 0, torch.float32: 1, torch.float64: 2}.get(self.raw_dtype)
+        if code is None:
+            raise RuntimeError(f"gcl_b200.data: stored dtype {self.raw_dtype} is not float16 / float32 / float64")
+        nlon, nlat = (self.grid_nodes, 1) if self.flat_grid else self.frame_shape[:2]
+        X = torch.empty((B, self.grid_nodes, self.obs_window * self.n_feat), dtype=torch.float32, device=self.device)
+        Y = torch.empty((B, self.grid_nodes, self.pred_steps * self.n_feat), dtype=torch.float32, device=self.device)
+        lib = _cabi.load()
+        with torch.cuda.device(self.device):
+            _cabi.check(lib.gcl_window_assemble(raw.data_ptr(), code, self.mean.data_ptr(), self.std.data_ptr(),
+                                                X.data_ptr(), Y.data_ptr(), B, window, self.obs_window, nlon, nlat,
+                                                self.n_feat_total, self.n_feat, int(self.flat_grid),
+                                                torch.cuda.current_stream(self.device).cuda_stream),
+                        "gcl_window_assemble")
+        return X, Y

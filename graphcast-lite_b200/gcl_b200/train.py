@@ -9,8 +9,9 @@ prediction, latitude-weighted MSE, Adam) for B samples per GPU:
   * samples shard over ranks (rank r takes its own B samples); graphs and weights are replicated.
     The reference has no multi-GPU code at all; effective batch = world x B.
 
-Static / forcing channel carry-forward (train.py:218-226) is not used by the BASELINE configs and is
-not implemented.
+Static / forcing channel carry-forward (train.py:218-226), the channel / spatial loss masks (train.py:85-102) and
+use_residual=False (train.py:203-207) are Trainer options; the whole per-step glue (residual add, masked weighted MSE,
+carry-forward, window slide) is one kernel forward (gcl_ar_step_f32) and one backward.
 """
 from typing import Optional
 
@@ -27,41 +28,54 @@ def lat_weights(nlat: int, nlon: int, device) -> torch.Tensor:
     return w.view(1, -1).expand(nlon, nlat).reshape(-1).contiguous().to(device)
 
 
-class _ResidualWMSE(torch.autograd.Function):
-    """(delta, x_last, y) -> (scale * weighted MSE, out = x_last + delta); gradient computed in forward."""
+class _ARStep(torch.autograd.Function):
+    """(delta [B,G,C], state [B,G,obs,C], y_step view) -> (scale * weighted MSE, new_state): residual add, masked
+    latitude-weighted MSE, static / forcing carry-forward and the window slide of train.py:201-227 in one kernel;
+    the backward (one kernel) returns d delta and d state."""
 
     @staticmethod
-    def forward(ctx, delta, x_last, y, lat_w, inv_wsum, scale, want_state):
+    def forward(ctx, delta, state, y, node_w, chan_w, carry, residual, inv_wsum, scale, want_state):
         lib = _cabi.load()
         d = delta.contiguous()
+        st = state.contiguous()
         B, G, C = d.shape
-        for t in (x_last, y):
-            if t.stride(2) != 1 or t.stride(0) != G * t.stride(1):
-                raise RuntimeError("gcl_b200: x_last / y must be [B,G,C] views with unit channel stride")
-        out = torch.empty_like(d) if want_state else None
-        grad = torch.empty_like(d)
+        obs = st.shape[2]
+        if st.shape != (B, G, obs, C):
+            raise RuntimeError(f"gcl_b200: state {tuple(st.shape)} does not match delta {tuple(d.shape)}")
+        if y.stride(2) != 1 or y.stride(0) != G * y.stride(1):
+            raise RuntimeError("gcl_b200: y must be a [B,G,C] view with unit channel stride")
+        new_state = torch.empty_like(st) if want_state else None
+        g_loss = torch.empty_like(d)
         loss = torch.empty(1, dtype=torch.float32, device=d.device)
         nb = lib.gcl_wmse_workspace_bytes(B, G, C)
         ws = torch.empty(nb, dtype=torch.uint8, device=d.device)
+        p = lambda t: t.data_ptr() if t is not None else None
         with torch.cuda.device(d.device):
-            _cabi.check(lib.gcl_wmse_f32(d.data_ptr(), x_last.data_ptr(), x_last.stride(1), y.data_ptr(), y.stride(1),
-                                         lat_w.data_ptr() if lat_w is not None else None, float(inv_wsum),
-                                         out.data_ptr() if out is not None else None, grad.data_ptr(),
-                                         loss.data_ptr(), 0, float(scale), B, G, C, ws.data_ptr(), nb,
-                                         torch.cuda.current_stream().cuda_stream), "gcl_wmse_f32")
-        ctx.save_for_backward(grad)
-        ctx.x_needs = ctx.needs_input_grad[1]
+            _cabi.check(lib.gcl_ar_step_f32(d.data_ptr(), st.data_ptr(), y.data_ptr(), y.stride(1), p(node_w), p(chan_w),
+                                            p(carry), int(bool(residual)), float(inv_wsum), float(scale), p(new_state),
+                                            g_loss.data_ptr(), loss.data_ptr(), 0, B, G, obs, C, ws.data_ptr(), nb,
+                                            torch.cuda.current_stream().cuda_stream), "gcl_ar_step_f32")
+        ctx.save_for_backward(g_loss, carry)
+        ctx.residual, ctx.shape, ctx.state_needs = bool(residual), (B, G, obs, C), ctx.needs_input_grad[1]
         if want_state:
-            return loss.squeeze(0), out
+            return loss.squeeze(0), new_state
         return loss.squeeze(0), None
 
     @staticmethod
-    def backward(ctx, dloss, dout=None):
-        (g,) = ctx.saved_tensors
-        d = g * dloss
-        if dout is not None:
-            d = d + dout
-        return d, (d if ctx.x_needs else None), None, None, None, None, None
+    def backward(ctx, dloss, dnew=None):
+        g_loss, carry = ctx.saved_tensors
+        B, G, obs, C = ctx.shape
+        lib = _cabi.load()
+        d_delta = torch.empty_like(g_loss)
+        d_state = torch.empty((B, G, obs, C), dtype=torch.float32, device=g_loss.device) if ctx.state_needs else None
+        dl = dloss.reshape(1).to(torch.float32).contiguous() if dloss is not None else None
+        dn = dnew.contiguous() if dnew is not None else None
+        p = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(g_loss.device):
+            _cabi.check(lib.gcl_ar_step_bwd_f32(g_loss.data_ptr(), p(dl), p(dn), p(carry), int(ctx.residual),
+                                                d_delta.data_ptr(), p(d_state), B, G, obs, C,
+                                                torch.cuda.current_stream().cuda_stream), "gcl_ar_step_bwd_f32")
+        return d_delta, d_state, None, None, None, None, None, None, None, None
 
 
 class Trainer:
@@ -69,7 +83,11 @@ class Trainer:
 
     def __init__(self, model: torch.nn.Module, nlat: int, nlon: int, lr: float = 1e-3, ar_steps: int = 1,
                  use_latitude_weighting: bool = True, use_residual: bool = True, betas=(0.9, 0.999),
-                 eps: float = 1e-8, process_group=None):
+                 eps: float = 1e-8, process_group=None, static_channels=(), forcing_channels=(),
+                 channel_mask: Optional[torch.Tensor] = None, spatial_mask: Optional[torch.Tensor] = None):
+        """static_channels / forcing_channels: channel indices carried forward from the last input step / taken from
+        the target during the rollout (train.py:218-226).  channel_mask [C], spatial_mask [G] (or the reference's
+        [1,G,1]): loss weights of weighted_mse_loss (train.py:85-102)."""
         self.model = model
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.ar_steps, self.use_residual = int(ar_steps), use_residual
@@ -107,7 +125,16 @@ class Trainer:
         self.flat_size = n                                   # incl. alignment padding
         self.lat_w = lat_weights(nlat, nlon, dev) if use_latitude_weighting else None
         self.G = nlat * nlon
-        self._wsum = float(self.lat_w.sum()) if self.lat_w is not None else float(self.G)  # one-time sync
+        # per-node loss weight = latitude weight x spatial mask; per-channel weight = channel mask
+        self.node_w = self.lat_w
+        if spatial_mask is not None:
+            sm = spatial_mask.to(dev, torch.float32).reshape(-1)
+            self.node_w = sm if self.node_w is None else (self.node_w * sm).contiguous()
+        self.chan_w = channel_mask.to(dev, torch.float32).reshape(-1).contiguous() if channel_mask is not None else None
+        self._wsum = float(self.node_w.sum()) if self.node_w is not None else float(self.G)  # one-time sync
+        self._csum = float(self.chan_w.sum()) if self.chan_w is not None else None
+        self.static_channels, self.forcing_channels = tuple(static_channels), tuple(forcing_channels)
+        self._carry = None
         if self.world > 1:   # identical replicas: take rank 0's initial weights
             dist.broadcast(self.flat_param, src=0, group=self.pg)
 
@@ -120,7 +147,17 @@ class Trainer:
         C = X.shape[-1] // obs
         tsteps = y.shape[-1] // C
         steps = min(self.ar_steps, tsteps)
-        wsum = self._wsum * B * C          # sum of all loss weights (train.py:101)
+        if self.chan_w is not None and self.chan_w.numel() != C:
+            raise ValueError(f"gcl_b200.Trainer: channel_mask has {self.chan_w.numel()} entries, the data {C} channels")
+        wsum = max(self._wsum * B * (C if self._csum is None else self._csum), 1e-12)   # train.py:101
+        if self._carry is None:
+            carry = torch.zeros(C, dtype=torch.int32)
+            for ch in self.static_channels:
+                carry[ch] = 1
+            for ch in self.forcing_channels:          # the reference applies forcing after static (train.py:222-226)
+                carry[ch] = 2
+            self._carry = carry.to(X.device) if (self.static_channels or self.forcing_channels) else False
+        carry = self._carry if self._carry is not False else None
         ys = y.view(B, G, tsteps, C)
         state = X.view(B, G, obs, C)
         total = None
@@ -128,14 +165,12 @@ class Trainer:
             delta = model(X=state.reshape(B, G, obs * C), attention_threshold=attention_threshold, **kwargs)
             if delta.dim() == 2:
                 delta = delta.unsqueeze(0)
-            if not self.use_residual:
-                raise NotImplementedError("gcl_b200.Trainer: use_residual=False is not used by the BASELINE configs")
             last = s == steps - 1
-            l, out = _ResidualWMSE.apply(delta, state[:, :, -1, :], ys[:, :, s, :], self.lat_w, 1.0 / wsum,
-                                         1.0 / steps, not last)
+            l, state_next = _ARStep.apply(delta, state, ys[:, :, s, :], self.node_w, self.chan_w, carry,
+                                          self.use_residual, 1.0 / wsum, 1.0 / steps, not last)
             total = l if total is None else total + l
             if not last:
-                state = torch.cat([state[:, :, 1:, :], out.unsqueeze(2)], dim=2)
+                state = state_next
         return total
 
     def zero_grad(self):
@@ -236,6 +271,13 @@ class Trainer:
         if next_batch is not None:
             self.prefetch(*next_batch)
         return float(loss.item())
+
+    def step_from_device(self, X: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """Captured step on device-resident tensors (what gcl_b200.data.ChunkedWindowLoader.batches() yields): two
+        device-to-device copies into the graph's input buffers, then the replay.  Returns the loss tensor (no sync)."""
+        self.static_x.copy_(X, non_blocking=True)
+        self.static_y.copy_(y, non_blocking=True)
+        return self.step_captured()
 
     def step(self, X: torch.Tensor, y: torch.Tensor, attention_threshold: float = 0.0, **kwargs) -> torch.Tensor:
         """forward + backward + gradient all-reduce + Adam; returns the (local) loss as a 0-d tensor."""

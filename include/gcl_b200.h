@@ -370,6 +370,46 @@ int gcl_wmse_f32(const float* delta, const float* x_last, int64_t xl_stride, con
                  int64_t y_stride, const float* lat_w, float inv_wsum, float* out_state,
                  float* d_delta, float* loss_out, int accumulate, float scale, int64_t batch,
                  int64_t n_grid, int64_t c, void* workspace, size_t workspace_bytes, void* stream);
+/* One autoregressive training step behind the model (train.py:201-227) in one pass over [B, G, C]:
+ *   out = (residual ? state[b,g,obs-1,:] : 0) + delta            (train.py:203-207)
+ *   loss += scale * sum w (out - y)^2 * inv_wsum,  w = node_w[g] * chan_w[c]   (weighted_mse_loss, train.py:85-102:
+ *           node_w = latitude weights x spatial mask, chan_w = channel mask; inv_wsum = 1 / max(sum of all w, 1e-12))
+ *   g_loss = d loss / d out  [B, G, C]
+ *   new_state [B, G, obs, C] (nullable) = window slide [state[.., 1:, :], out'] with the carry-forward of
+ *           train.py:218-227: out'[c] = state[.., obs-1, c] where carry[c] == 1 (static channel), y[c] where
+ *           carry[c] == 2 (forcing channel), out[c] otherwise.  carry nullable (= all 0).
+ *   y nullable (inference rollout without ground truth: no forcing values, the loss is meaningless).
+ * gcl_ar_step_bwd_f32: given d loss (device scalar, nullable = 1) and d new_state (nullable), d_delta [B, G, C] and
+ *   d_state [B, G, obs, C] (nullable).  Workspace as gcl_wmse_f32. */
+int gcl_ar_step_f32(const float* delta, const float* state, const float* y, int64_t y_stride,
+                    const float* node_w, const float* chan_w, const int32_t* carry, int residual,
+                    float inv_wsum, float scale, float* new_state, float* g_loss, float* loss_out,
+                    int accumulate, int64_t batch, int64_t n_grid, int64_t obs, int64_t c, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int gcl_ar_step_bwd_f32(const float* g_loss, const float* dloss, const float* d_new_state, const int32_t* carry,
+                        int residual, float* d_delta, float* d_state, int64_t batch, int64_t n_grid, int64_t obs,
+                        int64_t c, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * f2  input pipeline, device side.  TimeseriesChunkDataset.__getitem__ (src/data/dataloader_chunked.py:179-223)
+ *   converts, normalises and transposes every window on CPU workers; here the host only stages RAW windows and one
+ *   kernel produces both model tensors for the whole batch:
+ *   raw [B, W, n_lon, n_lat, f_total] (flat = 0) or [B, W, N, f_total] (flat = 1, pass n_lon = N, n_lat = 1) in the
+ *   dataset's stored dtype; x_out [B, G, obs * f_used], y_out [B, G, (W - obs) * f_used], G lat-major
+ *   (node = lat * n_lon + lon);  value = (float32(raw) - mean[f]) / std[f], the reference's float32 operations.
+ */
+#define GCL_RAW_F16 0
+#define GCL_RAW_F32 1
+#define GCL_RAW_F64 2
+int gcl_window_assemble(const void* raw, int raw_dtype, const float* mean, const float* stdv, float* x_out,
+                        float* y_out, int64_t batch, int64_t window, int64_t obs, int64_t n_lon, int64_t n_lat,
+                        int64_t f_total, int64_t f_used, int flat, void* stream);
+/* f4  streaming forecast metrics (scripts/predict.py:53-124, StreamingMetrics.update) for a batch:
+ *   y_true, y_pred [B, G, cols]; out float64 [B, cols, 3] = {sum_g err^2, sum_g |err|, spatial anomaly correlation
+ *   <yt - mean, yp - mean> / (|yt - mean| |yp - mean| + 1e-8)}; float64 accumulation, fixed summation order. */
+size_t gcl_forecast_metrics_workspace_bytes(int64_t batch, int64_t cols);
+int gcl_forecast_metrics_f32(const float* y_true, const float* y_pred, double* out, int64_t batch, int64_t n_grid,
+                             int64_t cols, void* workspace, size_t workspace_bytes, void* stream);
+
 /* torch.optim.Adam (main.py:212; betas/eps defaults, weight_decay 0) over one flat fp32 buffer.
  * step_count: device int32[1], incremented by the kernel (graph-replay safe). grad_scale multiplies g. */
 int gcl_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

@@ -179,18 +179,25 @@ def lat_weights(nlat: int, nlon: int) -> torch.Tensor:
     return w.view(1, -1).expand(nlon, nlat).reshape(-1).view(1, -1, 1)
 
 
-def weighted_mse(pred, target, lat_w=None):
-    """train.py:85-102 without channel / spatial masks (BASELINE configs set none)."""
+def weighted_mse(pred, target, lat_w=None, channel_mask=None, spatial_mask=None):
+    """train.py:85-102: squared error weighted by channel mask [C], spatial mask [1,G,1] and latitude weights
+    [1,G,1], normalised by the sum of the weights."""
     diff = (pred - target) ** 2
     w = torch.ones_like(diff)
+    if channel_mask is not None:
+        w = w * channel_mask.view(1, 1, -1)
+    if spatial_mask is not None:
+        w = w * spatial_mask
     if lat_w is not None:
         w = w * lat_w
     return (diff * w).sum() / w.sum().clamp_min(1e-12)
 
 
 def training_loss(model: WeatherPrediction, X, y, ar_steps: int, lat_w=None, threshold=0.0,
-                  use_residual=True, **kwargs):
-    """Loss of one train_epoch iteration (train.py:173-231): AR rollout, BPTT through it."""
+                  use_residual=True, static_channels=(), forcing_channels=(), channel_mask=None, spatial_mask=None,
+                  **kwargs):
+    """Loss of one train_epoch iteration (train.py:173-231): AR rollout with static / forcing carry-forward
+    (:218-226), BPTT through it."""
     if X.dim() == 2:
         X, y = X.unsqueeze(0), y.unsqueeze(0)
     Bn, G, _ = X.shape
@@ -206,6 +213,14 @@ def training_loss(model: WeatherPrediction, X, y, ar_steps: int, lat_w=None, thr
         if delta.dim() == 2:
             delta = delta.unsqueeze(0)
         out = state[:, :, -1, :] + delta if use_residual else delta
-        loss = loss + weighted_mse(out, ys[:, :, s, :], lat_w)
+        loss = loss + weighted_mse(out, ys[:, :, s, :], lat_w, channel_mask, spatial_mask)
+        if static_channels:
+            static_vals = state[:, :, -1, :]
+            for ch in static_channels:
+                out[:, :, ch] = static_vals[:, :, ch]
+        if forcing_channels and s < tsteps:
+            forcing_vals = ys[:, :, s, :]
+            for ch in forcing_channels:
+                out[:, :, ch] = forcing_vals[:, :, ch]
         state = torch.cat([state[:, :, 1:, :], out.unsqueeze(2)], dim=2)
     return loss / steps

@@ -44,3 +44,25 @@ def test_prefetching_iterator_on_device(tmp_path):
     for k, (x, y) in enumerate(got):
         xr, yr = ld.batch(range(5 * k, min(5 * k + 5, n)))
         assert torch.equal(x, xr) and torch.equal(y, yr), k
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_legacy_chunks_of_other_float_dtypes_on_device(tmp_path, dtype):
+    """chunk_*.npy stored as float32 / float64 (values beyond float16's range): the kernel converts like the
+    reference's .astype(np.float32) (dataloader_chunked.py:190) -- bit-exact, nothing quantised."""
+    from gcl_b200.data import ChunkedWindowLoader
+    rng = np.random.default_rng(5)
+    T, lon, lat, F = 9, 5, 3, 4
+    np.savez(os.path.join(tmp_path, "scalers.npz"), mean=rng.normal(size=F).astype(np.float32),
+             std=(0.5 + rng.random(F)).astype(np.float32), n=np.int64(T))
+    a = (rng.normal(size=(T, lon, lat, F)) * 1e5).astype(dtype)
+    np.save(os.path.join(tmp_path, "chunk_0.npy"), a)
+    ld = ChunkedWindowLoader(str(tmp_path), 2, 1, "all", None, device="cuda:0")
+    X, Y = ld.batch([0, 3])
+    sc = np.load(os.path.join(tmp_path, "scalers.npz"))
+    for b, t in enumerate((0, 3)):
+        w = (a[t:t + 3].astype(np.float32) - sc["mean"]) / sc["std"]
+        w = w.transpose(2, 1, 0, 3).reshape(lon * lat, 3, F)
+        assert np.array_equal(X[b].cpu().numpy(), w[:, :2].reshape(lon * lat, 2 * F))
+        assert np.array_equal(Y[b].cpu().numpy(), w[:, 2:].reshape(lon * lat, F))
+        assert np.isfinite(X[b].cpu().numpy()).all()

@@ -181,6 +181,73 @@ def test_forecast_step_and_gradients_full_size(name, engine):
     assert checked > 0
 
 
+def _kink_free_inputs(ref, make, run, floor, seeds):
+    """Inputs whose smallest |PReLU input| anywhere in the oracle's forward is > floor: a pre-activation within fp32
+    rounding of 0 may take different PReLU branches in two equally accurate evaluations and then moves a weight
+    gradient by ~1/sqrt(rows) -- not a kernel error.  Returns the first such seed's inputs."""
+    seen = []
+    hooks = [m.register_forward_hook(lambda mod, inp, out: seen.append(float(inp[0].detach().abs().min())))
+             for m in ref.modules() if isinstance(m, torch.nn.PReLU)]
+    try:
+        best = None
+        for seed in seeds:
+            data = make(seed)
+            seen.clear()
+            with torch.no_grad():
+                run(*data)
+            if best is None or min(seen) > best[0]:
+                best = (min(seen), data)
+            if min(seen) > floor:
+                break
+    finally:
+        for h in hooks:
+            h.remove()
+    return best
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_tcgen05_engine_gradients_within_1e4_of_fp32_oracle_on_kink_free_inputs(name):
+    """The DEFAULT dense engine (tcgen05 3xTF32) held to the plain north-star bar -- output, loss and EVERY gradient
+    within rel 1e-4 of the fp32 oracle -- for the architectures of all five BASELINE configs (their widths, layer
+    types and depths; 32x16 grid, mesh [1,3], B = 2 samples so that every dense layer has >= 2048 rows and takes the
+    tensor-core kernels), on inputs chosen to keep every PReLU input away from its kink."""
+    from gcl_b200 import _cabi
+    from gcl_b200.train import Trainer
+    from oracle import model as om
+    _set_engine("tcgen05")
+    assert _cabi.load().gcl_get_dense_mode() == 0
+    kw = dict(batch_num=1) if name == "sparse_attention" else {}
+    B = 2
+    # the mesh rows of the encoder input are constants (static features), so some PReLU inputs do not depend on the
+    # data seed: the weight seed is part of the search
+    for wseed in range(11, 19):
+        mine, ref, cfg, nlat, nlon = _models(name, 16, 32, [1, 3], 0.6, seed=wseed)
+        G = nlat * nlon
+        F, T = cfg["data"]["num_features_used"], cfg["data"]["obs_window_used"]
+        assert B * (G + mine._num_mesh_nodes) >= 2048
+        lw = om.lat_weights(nlat, nlon)
+
+        def make(seed):
+            gen = torch.Generator().manual_seed(seed)
+            return torch.randn(B, G, T * F, generator=gen), torch.randn(B, G, F, generator=gen)
+        floor, (X, y) = _kink_free_inputs(ref, make, lambda X, y: om.training_loss(ref, X, y, 1, lw, **kw), 5e-7,
+                                          range(100, 140))
+        if floor > 1e-7:
+            break
+    assert floor > 1e-7, f"no kink-free input found (best floor {floor:.1e})"
+    out_g = mine(X=X.to(DEV), attention_threshold=0.0, **kw)
+    out_c = ref(X=X, attention_threshold=0.0, **kw)
+    assert_close(out_g, out_c, RTOL_F32, f"{name} forecast step (tcgen05)")
+    tr = Trainer(mine, nlat, nlon, lr=cfg["learning_rate"], ar_steps=1)
+    tr.zero_grad()
+    lg = tr.loss(X.to(DEV), y.to(DEV), 0.0, **kw)
+    lg.backward()
+    lc = om.training_loss(ref, X, y, 1, lw, **kw)
+    lc.backward()
+    assert abs(float(lg.detach()) - float(lc.detach())) <= RTOL_F32 * abs(float(lc.detach()))
+    _check_grads(mine, ref, RTOL_F32, f"{name} (tcgen05, kink-free)")
+
+
 @pytest.mark.parametrize("name", ["baseline", "attention", "sparse_attention"])
 def test_against_unmodified_reference_fixture(name, golden_dir):
     """Product vs what the UNMODIFIED reference computed (tests/golden/model_*.npz)."""
@@ -410,3 +477,50 @@ def test_import_swap_reference_glue_on_gcl_layers():
         a.square().mean().backward()
         b.square().mean().backward()
         _check_grads(sw, ref, RTOL_F32, f"import-swap {name}")
+
+
+@pytest.mark.parametrize("residual", [True, False])
+def test_ar_rollout_with_static_forcing_channels_and_loss_masks(residual):
+    """train_epoch semantics beyond the BASELINE configs (train.py:85-102, 203-207, 218-226): static channels carried
+    forward, forcing channels taken from the target, channel / spatial loss masks, use_residual on and off; AR = 3
+    with BPTT, against the oracle's restated loop."""
+    from gcl_b200.train import Trainer
+    from oracle import model as om
+    mine, ref, cfg, nlat, nlon = _models("wb2_64x32_ar_15f_4obs_4pred", 16, 32, [1, 3], 0.6, seed=21)
+    G, F, T = nlat * nlon, 15, 4
+    static, forcing = (2, 7), (0, 11)
+    cmask = torch.ones(F)
+    cmask[list(static)] = 0.0
+    smask = torch.zeros(nlon, nlat)
+    smask[2:nlon - 2, 1:nlat - 1] = 1.0                  # build_boundary_mask layout (train.py:74-83)
+    smask = smask.reshape(1, -1, 1)
+    lw = om.lat_weights(nlat, nlon)
+
+    def make(seed):
+        gen = torch.Generator().manual_seed(seed)
+        return torch.randn(2, G, T * F, generator=gen), torch.randn(2, G, 4 * F, generator=gen)
+    kwargs = dict(use_residual=residual, static_channels=static, forcing_channels=forcing, channel_mask=cmask,
+                  spatial_mask=smask)
+    floor, (X, y) = _kink_free_inputs(ref, make, lambda X, y: om.training_loss(ref, X, y, 3, lw, **kwargs), 1e-6,
+                                      range(40, 90))
+    tr = Trainer(mine, nlat, nlon, ar_steps=3, use_residual=residual, static_channels=static, forcing_channels=forcing,
+                 channel_mask=cmask, spatial_mask=smask)
+    tr.zero_grad()
+    lg = tr.loss(X.to(DEV), y.to(DEV))
+    lg.backward()
+    lc = om.training_loss(ref, X, y, 3, lw, **kwargs)
+    lc.backward()
+    assert abs(float(lg) - float(lc)) <= RTOL_F32 * abs(float(lc)), (float(lg), float(lc))
+    _check_grads(mine, ref, RTOL_F32, f"AR=3 masks residual={residual}")
+    # the carried state itself: static channels keep the input's last step, forcing channels follow the target
+    from gcl_b200.train import _ARStep
+    delta = torch.randn(2, G, F, device=DEV)
+    st = X.to(DEV).view(2, G, T, F)
+    _, new = _ARStep.apply(delta, st, y.to(DEV).view(2, G, 4, F)[:, :, 1, :], tr.node_w, tr.chan_w, tr._carry,
+                           residual, 1.0, 1.0, True)
+    assert torch.equal(new[:, :, :-1], st[:, :, 1:])
+    assert torch.equal(new[:, :, -1, list(static)], st[:, :, -1, list(static)])
+    assert torch.equal(new[:, :, -1, list(forcing)], y.to(DEV).view(2, G, 4, F)[:, :, 1, list(forcing)])
+    free = [c for c in range(F) if c not in static + forcing]
+    want = delta[:, :, free] + (st[:, :, -1, free] if residual else 0)
+    assert torch.equal(new[:, :, -1, free], want)

@@ -225,3 +225,32 @@ def test_model_glue_matches_unmodified_reference(name):
     b = mine(X=X, attention_threshold=thr, **kw)
     assert torch.equal(a, b)
     assert torch.equal(ref.processing_graph, mine.processing_graph)
+
+
+@pytest.mark.reference
+def test_oracle_loss_matches_the_reference_functions():
+    """oracle.model.weighted_mse / lat_weights against the UNMODIFIED weighted_mse_loss / get_lat_weights /
+    build_boundary_mask of /root/reference/src/train.py (their source is executed as is; the module itself cannot be
+    imported: wandb is not installed), with channel and spatial masks."""
+    import ast
+    import numpy as np
+    import torch
+    from oracle import model as om
+    src = open("/root/reference/src/train.py").read()
+    tree = ast.parse(src)
+    wanted = {"get_lat_weights", "build_boundary_mask", "weighted_mse_loss"}
+    code = "\n\n".join(ast.get_source_segment(src, n) for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted)
+    ns = {"torch": torch, "np": np}
+    exec(compile(code, "reference_train_excerpt", "exec"), ns)
+    gen = torch.Generator().manual_seed(0)
+    nlat, nlon, C = 6, 8, 5
+    pred, tgt = torch.randn(3, nlat * nlon, C, generator=gen), torch.randn(3, nlat * nlon, C, generator=gen)
+    lw_ref = ns["get_lat_weights"](nlat, nlon, "cpu")
+    assert torch.equal(om.lat_weights(nlat, nlon), lw_ref)
+    cm = torch.tensor([1.0, 0.0, 1.0, 1.0, 0.0])
+    sm = ns["build_boundary_mask"](nlon, nlat, 1, "cpu")
+    for kw in (dict(), dict(channel_mask=cm), dict(spatial_mask=sm), dict(channel_mask=cm, spatial_mask=sm)):
+        a = om.weighted_mse(pred, tgt, lw_ref, **kw)
+        b = ns["weighted_mse_loss"](pred, tgt, lw_ref, **kw)
+        assert torch.equal(a, b), kw
+    assert torch.equal(om.weighted_mse(pred, tgt), ns["weighted_mse_loss"](pred, tgt))
