@@ -367,7 +367,9 @@ def bench_workload(name, args, world, rank, dev, ar_steps=1, batch=0, headline=F
                    "l2": f"one activation tensor is {act_mb:.0f} MB per step and ~60 are live (> 126 MB L2): "
                          "inputs larger than L2, no flush needed",
                    "cuda_graph": ("off (--no-graph, profiling run)" if args.no_graph
-                                  else "fwd+bwd captured; all-reduce + Adam eager"),
+                                  else ("whole step captured: fwd + bwd + gradient all-reduce + Adam = one graph launch"
+                                        if getattr(tr, "_graph_has_tail", False)
+                                        else "fwd+bwd captured; all-reduce + Adam eager")),
                    "vs_cpu": "the GPU arm batches B samples per step; the reference (and the CPU port beside it) is "
                              "batch-1 only (models.py:822), so both are compared in samples/s"},
         "clocks": clocks,

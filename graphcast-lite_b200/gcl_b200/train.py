@@ -205,10 +205,12 @@ class Trainer:
                         "gcl_adam_f32")
 
     # -- CUDA-graph fast path: forward + backward of a fixed batch shape captured once, replayed per step
-    def capture(self, batch: int, tf: int, yf: int, attention_threshold: float = 0.0, warmup: int = 2):
-        """Allocate static input buffers [batch, G, tf] / [batch, G, yf] and capture forward + backward (+ the
-        multi-tensor gradient copy) into one CUDA graph (every gcl_* entry point is enqueue-only).  The gradient all-reduce
-        and Adam stay outside the graph (one NCCL call + two tiny kernels)."""
+    def capture(self, batch: int, tf: int, yf: int, attention_threshold: float = 0.0, warmup: int = 2,
+                whole_step: bool = True):
+        """Allocate static input buffers [batch, G, tf] / [batch, G, yf] and capture the training step into one CUDA
+        graph (every gcl_* entry point is enqueue-only).  whole_step: the gradient all-reduce (NCCL, one flat bucket)
+        and the Adam kernel are captured too, so a step is ONE graph launch; if the collective cannot be captured on
+        this build the graph ends after the backward and the tail runs eagerly (one NCCL call + two tiny kernels)."""
         dev = self.flat_param.device
         self.static_x = torch.zeros(batch, self.G, tf, dtype=torch.float32, device=dev)
         self.static_y = torch.zeros(batch, self.G, yf, dtype=torch.float32, device=dev)
@@ -219,22 +221,44 @@ class Trainer:
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):      # builds the CSR caches (they sync) before capture
                 self.backward(self.loss(self.static_x, self.static_y, attention_threshold))
+                if whole_step and self.world > 1:            # the communicator must exist before capture
+                    dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         lib = _cabi.load()
-        before = lib.gcl_launch_count()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self.loss(self.static_x, self.static_y, attention_threshold)
-            self.backward(self.static_loss)
-        self.launches_in_graph = int(lib.gcl_launch_count() - before)
+
+        def record(tail: bool):
+            before = lib.gcl_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.static_loss = self.loss(self.static_x, self.static_y, attention_threshold)
+                self.backward(self.static_loss)
+                if tail:
+                    self.reduce_gradients()
+                    self.optimizer_step()
+            return g, int(lib.gcl_launch_count() - before)
+
+        saved = (self.flat_param.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_count.clone())
+        self._graph_has_tail = False
+        if whole_step:
+            try:
+                self.graph, self.launches_in_graph = record(True)
+                self._graph_has_tail = True
+            except RuntimeError:                              # e.g. a NCCL build that refuses stream capture
+                torch.cuda.synchronize(dev)
+        if not self._graph_has_tail:
+            self.graph, self.launches_in_graph = record(False)
+        # capture does not execute, but keep the optimiser state exactly as it was in any case
+        for dst, src in zip((self.flat_param, self.exp_avg, self.exp_avg_sq, self.step_count), saved):
+            dst.copy_(src)
         return self
 
     def step_captured(self) -> torch.Tensor:
         """One training step on whatever is in static_x / static_y (device resident)."""
         self.graph.replay()
-        self.reduce_gradients()
-        self.optimizer_step()
+        if not self._graph_has_tail:
+            self.reduce_gradients()
+            self.optimizer_step()
         return self.static_loss
 
     def prefetch(self, X_pinned: torch.Tensor, y_pinned: torch.Tensor):

@@ -381,8 +381,8 @@ def test_cuda_graph_capture_of_forward_backward():
     gen = torch.Generator().manual_seed(6)
     X, y = torch.randn(2, G, T * F, generator=gen).to(DEV), torch.randn(2, G, F, generator=gen).to(DEV)
     tr = Trainer(mine, nlat, nlon, ar_steps=1)
-    tr.capture(2, T * F, F)
-    assert tr.launches_in_graph > 50
+    tr.capture(2, T * F, F, whole_step=False)      # forward + backward only: comparable with plain autograd
+    assert tr.launches_in_graph > 50 and not tr._graph_has_tail
     tr.static_x.copy_(X)
     tr.static_y.copy_(y)
     for v in tr._grad_views:
@@ -400,6 +400,22 @@ def test_cuda_graph_capture_of_forward_backward():
     # the full captured step also moves the weights (Adam) and leaves the loss readable
     tr.step_captured()
     assert not torch.equal(tr.flat_param, p0) and int(tr.step_count.item()) == 1
+    # whole-step graph (the default): ONE replay = forward + backward + (all-reduce) + Adam, bit-identical to the
+    # eager step from the same optimiser state
+    state = [t.clone() for t in (tr.flat_param, tr.exp_avg, tr.exp_avg_sq, tr.step_count)]
+    n_fb = tr.launches_in_graph
+    tr.capture(2, T * F, F)
+    assert tr._graph_has_tail and tr.launches_in_graph == n_fb + 2
+    assert all(torch.equal(a, b) for a, b in zip(state, (tr.flat_param, tr.exp_avg, tr.exp_avg_sq, tr.step_count)))
+    tr.static_x.copy_(X)
+    tr.static_y.copy_(y)
+    tr.step_captured()
+    torch.cuda.synchronize()
+    after_graph = tr.flat_param.clone()
+    for dst, src in zip((tr.flat_param, tr.exp_avg, tr.exp_avg_sq, tr.step_count), state):
+        dst.copy_(src)
+    tr.step(X, y)
+    assert torch.equal(tr.flat_param, after_graph) and int(tr.step_count.item()) == 2
     # end-to-end entry: pinned host batch in, loss out; a prefetched batch is consumed from the staging buffers
     hx, hy = X.cpu().pin_memory(), y.cpu().pin_memory()
     l1 = tr.step_from_host(hx, hy, next_batch=(hx, hy))
@@ -407,7 +423,7 @@ def test_cuda_graph_capture_of_forward_backward():
     tr.static_x.zero_()
     l2 = tr.step_from_host(hx, hy)
     assert not tr._has_staged and torch.equal(tr.static_x, X)
-    assert l1 > 0 and l2 > 0 and l2 < l1 and int(tr.step_count.item()) == 3
+    assert l1 > 0 and l2 > 0 and l2 < l1 and int(tr.step_count.item()) == 4
 
 
 def test_device_resident_rollout_and_metrics_match_oracle():
