@@ -172,39 +172,40 @@ __global__ void __launch_bounds__(kTileThreads)
   }
 }
 
-// Rows with more entries than a tile may hold: one CTA per (row, sample); warp w takes entries beg + w, beg + w + 8,
-// ... (a fixed assignment), the 8 partial rows are summed in warp order -> deterministic, no atomics.
-__global__ void __launch_bounds__(256)
+// Rows with more entries than a tile may hold: one CTA of 32 warps per (row, sample).  A group of GS lanes (one
+// 128-bit word each, GS = 4..32 >= words per row) takes entries beg + g, beg + g + n_groups, ... (a fixed
+// assignment), the partial rows are summed in group order -> deterministic, no atomics.
+constexpr int kHeavyThreads = 1024;
+template <int GS>
+__global__ void __launch_bounds__(kHeavyThreads)
     spmm_heavy_kernel(const int32_t* __restrict__ heavy_rows, const int32_t* __restrict__ rowptr,
                       const int32_t* __restrict__ col, const float* __restrict__ w, const float* __restrict__ x,
                       float* __restrict__ out, int64_t n_in, int C, int64_t x_bstride, int64_t out_bstride,
                       const float* __restrict__ bias, const float* __restrict__ prelu_slope, float* __restrict__ z_out) {
   extern __shared__ __align__(128) unsigned char smem[];
-  float4* part = reinterpret_cast<float4*>(smem);          // [8][words]
+  constexpr int NG = kHeavyThreads / GS;
+  float4* part = reinterpret_cast<float4*>(smem);          // [NG][words]
   const int words = C >> 2;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = threadIdx.x & (GS - 1), g = threadIdx.x / GS;
   const int64_t row = heavy_rows[blockIdx.x];
   const int b = blockIdx.y;
   const int32_t beg = rowptr[row], end = rowptr[row + 1];
-  const float* xb = x + (int64_t)b * x_bstride;
-  for (int w0 = 0; w0 < words; w0 += 32) {
-    const int wd = w0 + lane;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (wd < words) {
+  const float* xb = x + (int64_t)b * x_bstride + gl * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (gl < words) {
 #pragma unroll 4
-      for (int32_t k = beg + warp; k < end; k += 8) {
-        const int32_t c = __ldg(col + k);
-        if (c < n_in) fma4(acc, w ? __ldg(w + k) : 1.f, ldg4(xb + (int64_t)c * C + wd * 4));
-      }
-      part[warp * words + wd] = acc;
+    for (int32_t k = beg + g; k < end; k += NG) {
+      const int32_t c = __ldg(col + k);
+      if (c < n_in) fma4(acc, w ? __ldg(w + k) : 1.f, ldg4(xb + (int64_t)c * C));
     }
+    part[g * words + gl] = acc;
   }
   __syncthreads();
   const float slope = prelu_slope ? __ldg(prelu_slope) : 0.f;
-  for (int wd = threadIdx.x; wd < words; wd += 256) {
+  if (threadIdx.x < words) {
+    const int wd = threadIdx.x;
     float4 a = part[wd];
-#pragma unroll
-    for (int q = 1; q < 8; ++q) {
+    for (int q = 1; q < NG; ++q) {
       const float4 t = part[q * words + wd];
       a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
     }
@@ -418,9 +419,15 @@ extern "C" int gcl_spmm_tiled_f32(const gcl_tile_plan* plan, const int32_t* ent,
   if (plan->n_heavy > 0) {
     GCL_CHECK_ARG(plan->heavy_rows, "gcl_spmm_tiled_f32: plan lists heavy rows but has no heavy_rows array");
     dim3 grid((unsigned)plan->n_heavy, (unsigned)batch);
-    spmm_heavy_kernel<<<grid, 256, 8 * channels * 4, s>>>(plan->heavy_rows, rowptr, col, w, x, out, n_rows_in,
-                                                           (int)channels, x_bstride, out_bstride, bias, prelu_slope,
-                                                           z_out);
+    const int words = (int)channels / 4;
+#define GCL_HEAVY(GS)                                                                                            \
+  spmm_heavy_kernel<GS><<<grid, kHeavyThreads, (kHeavyThreads / GS) * channels * 4, s>>>(                         \
+      plan->heavy_rows, rowptr, col, w, x, out, n_rows_in, (int)channels, x_bstride, out_bstride, bias, prelu_slope, z_out)
+    if (words <= 4) GCL_HEAVY(4);
+    else if (words <= 8) GCL_HEAVY(8);
+    else if (words <= 16) GCL_HEAVY(16);
+    else GCL_HEAVY(32);
+#undef GCL_HEAVY
     GCL_CHECK_LAUNCH("gcl_spmm_tiled_f32(heavy rows)");
   }
   return GCL_OK;

@@ -185,6 +185,19 @@ __global__ void rows_cat_kernel(const T* __restrict__ a_c, const T* __restrict__
   }
 }
 
+// y[r, 0:c_out] = x[r, 0:min(c_in, c_out)], zero beyond: the slice that drops a layer's alignment padding, and its
+// backward (zero padding) -- one pass instead of torch's zero fill + strided copy
+__global__ void resize_channels_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int c_in,
+                                       int c_out) {
+  const int64_t total = rows * c_out;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / c_out;
+    const int c = (int)(i - r * c_out);
+    y[i] = c < c_in ? x[r * c_in + c] : 0.f;
+  }
+}
+
 int blocks_for(int64_t n) {
   int64_t b = ceil_div(n, kT);
   return (int)(b < 1 ? 1 : (b > kMaxBlocks ? kMaxBlocks : b));
@@ -326,5 +339,14 @@ extern "C" int gcl_ar_step_bwd_f32(const float* g_loss, const float* dloss, cons
   ar_step_bwd_kernel<<<blocks_for(total), kT, 0, static_cast<cudaStream_t>(stream)>>>(
       g_loss, dloss, d_new_state, carry, residual, d_delta, d_state, (int)obs, (int)c, total);
   GCL_CHECK_LAUNCH("gcl_ar_step_bwd_f32");
+  return GCL_OK;
+}
+
+extern "C" int gcl_resize_channels_f32(const float* x, float* y, int64_t rows, int64_t c_in, int64_t c_out, void* stream) {
+  GCL_CHECK_ARG(x && y && rows >= 0 && c_in > 0 && c_out > 0, "gcl_resize_channels_f32: bad argument");
+  if (rows == 0) return GCL_OK;
+  resize_channels_kernel<<<blocks_for(rows * c_out), kT, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rows, (int)c_in,
+                                                                                               (int)c_out);
+  GCL_CHECK_LAUNCH("gcl_resize_channels_f32");
   return GCL_OK;
 }

@@ -68,6 +68,7 @@ _PROTOS = {
     "gcl_window_assemble": (c_int, [P, I32, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, P]),
     "gcl_forecast_metrics_workspace_bytes": (SZ, [I64, I64]),
     "gcl_forecast_metrics_f32": (c_int, [P, P, P, I64, I64, I64, P, SZ, P]),
+    "gcl_resize_channels_f32": (c_int, [P, P, I64, I64, I64, P]),
     "gcl_adam_f32": (c_int, [P, P, P, P, I64, F32, F32, F32, F32, F32, P, P]),
 }
 

@@ -163,7 +163,7 @@ class GraphLayer(nn.Module):
                 X = ops.aggregate(h, g, NORM_GCN, b, nxt.weight if fuse else None,     # + bias + PReLU fused
                                   rows_out if last else None)
                 if C % 4:
-                    X = X[..., :C]
+                    X = ops.resize_channels(X, C)
                 i += 2 if fuse else 1
             elif type(m) is GATConv:
                 if fuse and m.heads == 1:                    # GATConv + the shared PReLU in one aggregation kernel

@@ -647,6 +647,36 @@ def split_rows(x, na: int):
     return _SplitRows.apply(x, na)
 
 
+class _ResizeChannels(torch.autograd.Function):
+    """x[..., :c] (c smaller: drop alignment padding) or zero-pad to c channels, contiguous result, one kernel each
+    way (torch's slice backward is a zero fill plus a strided copy)."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        xc = _chk(x, "x")
+        ctx.c_in = xc.shape[-1]
+        rows = xc.numel() // max(ctx.c_in, 1)
+        y = torch.empty(xc.shape[:-1] + (int(c),), dtype=torch.float32, device=xc.device)
+        with torch.cuda.device(xc.device):
+            _call("gcl_resize_channels_f32", _p(xc), _p(y), rows, ctx.c_in, int(c), _stream(),
+                  nbytes=4 * rows * (ctx.c_in + int(c)), tag=f"R{rows}x{ctx.c_in}->{int(c)}")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        d = _chk(dy, "grad_out")
+        rows = d.numel() // d.shape[-1]
+        dx = torch.empty(d.shape[:-1] + (ctx.c_in,), dtype=torch.float32, device=d.device)
+        with torch.cuda.device(d.device):
+            _call("gcl_resize_channels_f32", _p(d), _p(dx), rows, d.shape[-1], ctx.c_in, _stream(),
+                  nbytes=4 * rows * (ctx.c_in + d.shape[-1]), tag=f"R{rows}x{d.shape[-1]}->{ctx.c_in}")
+        return dx, None
+
+
+def resize_channels(x, c: int):
+    return _ResizeChannels.apply(x, c)
+
+
 def edge_prune(ei_pyg: torch.Tensor, alpha_pyg: torch.Tensor, threshold: float) -> torch.Tensor:
     """SparseGATConv pruning (models.py:140-149): edges with alpha >= threshold, order preserved."""
     if not ei_pyg.is_cuda or not alpha_pyg.is_cuda:

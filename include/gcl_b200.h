@@ -370,6 +370,9 @@ int gcl_wmse_f32(const float* delta, const float* x_last, int64_t xl_stride, con
                  int64_t y_stride, const float* lat_w, float inv_wsum, float* out_state,
                  float* d_delta, float* loss_out, int accumulate, float scale, int64_t batch,
                  int64_t n_grid, int64_t c, void* workspace, size_t workspace_bytes, void* stream);
+/* y [rows, c_out] = x [rows, c_in] truncated or zero-padded along the channel axis: drops the alignment padding of
+ * a layer computed 4-aligned (c_out < c_in) and, as its backward, re-pads the gradient (c_out > c_in). */
+int gcl_resize_channels_f32(const float* x, float* y, int64_t rows, int64_t c_in, int64_t c_out, void* stream);
 /* One autoregressive training step behind the model (train.py:201-227) in one pass over [B, G, C]:
  *   out = (residual ? state[b,g,obs-1,:] : 0) + delta            (train.py:203-207)
  *   loss += scale * sum w (out - y)^2 * inv_wsum,  w = node_w[g] * chan_w[c]   (weighted_mse_loss, train.py:85-102:
