@@ -220,6 +220,63 @@ __global__ void __launch_bounds__(kHeavyThreads)
   }
 }
 
+// bf16 rows: a lane owns one 16-byte word = 8 channels (fp32 accumulation, bf16 result)
+template <int GS>
+__global__ void __launch_bounds__(kHeavyThreads)
+    spmm_heavy_bf16_kernel(const int32_t* __restrict__ heavy_rows, const int32_t* __restrict__ rowptr,
+                           const int32_t* __restrict__ col, const float* __restrict__ w,
+                           const unsigned char* __restrict__ x, unsigned char* __restrict__ out, int64_t n_in, int C,
+                           int64_t x_bstride, int64_t out_bstride, const float* __restrict__ bias,
+                           const float* __restrict__ prelu_slope, unsigned char* __restrict__ z_out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NG = kHeavyThreads / GS;
+  float4* part = reinterpret_cast<float4*>(smem);          // [NG][words][2]
+  const int words = C >> 3;
+  const int gl = threadIdx.x & (GS - 1), g = threadIdx.x / GS;
+  const int64_t row = heavy_rows[blockIdx.x];
+  const int b = blockIdx.y;
+  const int32_t beg = rowptr[row], end = rowptr[row + 1];
+  const unsigned char* xb = x + ((int64_t)b * x_bstride) * 2 + gl * 16;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  if (gl < words) {
+#pragma unroll 4
+    for (int32_t k = beg + g; k < end; k += NG) {
+      const int32_t c = __ldg(col + k);
+      if (c < n_in) {
+        const float wk = w ? __ldg(w + k) : 1.f;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)c * C * 2));
+        fma4(a0, wk, bf16x4_lo(u));
+        fma4(a1, wk, bf16x4_hi(u));
+      }
+    }
+    part[(g * words + gl) * 2] = a0;
+    part[(g * words + gl) * 2 + 1] = a1;
+  }
+  __syncthreads();
+  const float slope = prelu_slope ? __ldg(prelu_slope) : 0.f;
+  if (threadIdx.x < words) {
+    const int wd = threadIdx.x;
+    float4 s0 = part[wd * 2], s1 = part[wd * 2 + 1];
+    for (int q = 1; q < NG; ++q) {
+      const float4 t0 = part[(q * words + wd) * 2], t1 = part[(q * words + wd) * 2 + 1];
+      s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
+      s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
+    }
+    if (bias) {
+      const float4 b0 = ldg4(bias + wd * 8), b1 = ldg4(bias + wd * 8 + 4);
+      s0.x += b0.x; s0.y += b0.y; s0.z += b0.z; s0.w += b0.w;
+      s1.x += b1.x; s1.y += b1.y; s1.z += b1.z; s1.w += b1.w;
+    }
+    const int64_t o = ((int64_t)b * out_bstride + row * C) * 2 + wd * 16;
+    if (z_out) *reinterpret_cast<uint4*>(z_out + o) = pack_bf16x8(s0, s1);
+    if (prelu_slope) {
+      s0 = ws_prelu4(s0, slope);
+      s1 = ws_prelu4(s1, slope);
+    }
+    *reinterpret_cast<uint4*>(out + o) = pack_bf16x8(s0, s1);
+  }
+}
+
 // samples per CTA: as many as keep the staged rows within ~64 KB (three CTAs per SM) and <= 4
 inline int tile_pick_sb(const TileArgs& p, int64_t C, int64_t B) {
   static const int cap = getenv("GCL_TILE_SB") ? atoi(getenv("GCL_TILE_SB")) : 4;
@@ -429,6 +486,51 @@ extern "C" int gcl_spmm_tiled_f32(const gcl_tile_plan* plan, const int32_t* ent,
     else GCL_HEAVY(32);
 #undef GCL_HEAVY
     GCL_CHECK_LAUNCH("gcl_spmm_tiled_f32(heavy rows)");
+  }
+  return GCL_OK;
+}
+
+extern "C" int gcl_spmm_tiled_bf16(const gcl_tile_plan* plan, const int32_t* ent, const int32_t* rowptr,
+                                  const int32_t* col, const float* w, const void* x, void* out, int64_t batch,
+                                  int64_t n_rows_in, int64_t channels, int64_t x_bstride, int64_t out_bstride,
+                                  const float* bias, const float* prelu_slope, void* z_out, void* stream) {
+  if (int rc = check_plan(plan, "gcl_spmm_tiled_bf16")) return rc;
+  GCL_CHECK_ARG(rowptr && col && x && out && x != out, "gcl_spmm_tiled_bf16: null or aliased pointer argument");
+  GCL_CHECK_ARG(plan->n_tiles == 0 || (ent && plan->tile_desc && al16(ent) && al16(plan->tile_desc)),
+                "gcl_spmm_tiled_bf16: the packed entries / tile descriptors are missing or not 16-byte aligned");
+  GCL_CHECK_ARG(plan->pad_entries == 2 || plan->pad_entries == 4 || plan->n_tiles == 0,
+                "gcl_spmm_tiled_bf16: the plan must be built with pad_entries = 2 or 4");
+  GCL_CHECK_ARG(channels > 0 && channels % 8 == 0 && channels <= 256 && x_bstride % 8 == 0 && out_bstride % 8 == 0 &&
+                    al16(x) && al16(out) && (!bias || al16(bias)) && (!z_out || al16(z_out)),
+                "gcl_spmm_tiled_bf16: needs 16-byte aligned rows of 8..256 bf16 channels (multiple of 8)");
+  GCL_CHECK_ARG(batch >= 0 && batch <= 65535 && n_rows_in > 0 && n_rows_in * channels < (1ll << 31),
+                "gcl_spmm_tiled_bf16: bad sizes");
+  if (batch == 0) return GCL_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (plan->n_tiles > 0) {
+    WsParams q{};
+    q.p = tile_args(plan);
+    q.ent = reinterpret_cast<const int2*>(ent);
+    q.x = static_cast<const float*>(x); q.x_bstride = x_bstride;          // element strides; the kernel scales by 2 bytes
+    q.out = static_cast<float*>(out); q.out_bstride = out_bstride; q.z_out = static_cast<float*>(z_out);
+    q.bias = bias; q.prelu_slope = prelu_slope;
+    q.C = (int)channels; q.B = (int)batch;
+    if (int rc = ws_dispatch_bf16(q, s, "gcl_spmm_tiled_bf16")) return rc;
+  }
+  if (plan->n_heavy > 0) {
+    GCL_CHECK_ARG(plan->heavy_rows, "gcl_spmm_tiled_bf16: plan lists heavy rows but has no heavy_rows array");
+    dim3 grid((unsigned)plan->n_heavy, (unsigned)batch);
+    const int words = (int)channels / 8;
+#define GCL_HEAVY16(GS)                                                                                          \
+  spmm_heavy_bf16_kernel<GS><<<grid, kHeavyThreads, (kHeavyThreads / GS) * words * 32, s>>>(                      \
+      plan->heavy_rows, rowptr, col, w, static_cast<const unsigned char*>(x), static_cast<unsigned char*>(out),   \
+      n_rows_in, (int)channels, x_bstride, out_bstride, bias, prelu_slope, static_cast<unsigned char*>(z_out))
+    if (words <= 4) GCL_HEAVY16(4);
+    else if (words <= 8) GCL_HEAVY16(8);
+    else if (words <= 16) GCL_HEAVY16(16);
+    else GCL_HEAVY16(32);
+#undef GCL_HEAVY16
+    GCL_CHECK_LAUNCH("gcl_spmm_tiled_bf16(heavy rows)");
   }
   return GCL_OK;
 }

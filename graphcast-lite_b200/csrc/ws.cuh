@@ -51,12 +51,12 @@ constexpr int kWsProducerThreads = 32 * kWsProducerWarps;
 struct WsSmem {
   int xs, ds, ent, wa, wb, dal, f2t, re, rid, desc, stage, us, rs, bars, total;   // byte offsets / sizes
 };
-inline WsSmem ws_smem(const TileArgs& p, int C, int SB, int mode) {
+inline WsSmem ws_smem(const TileArgs& p, int C, int SB, int mode, int elem_bytes = 4) {
   WsSmem s;
   const int E = (p.max_entries + 3) & ~3, R = p.max_rows, U = p.max_union;
   int o = 0;
-  s.xs = o;   o += SB * (U + 1) * C * 4;
-  s.ds = o;   o += mode == 3 ? SB * R * C * 4 : 0;
+  s.xs = o;   o += SB * (U + 1) * C * elem_bytes;
+  s.ds = o;   o += mode == 3 ? SB * R * C * elem_bytes : 0;
   s.ent = o;  o += E * 8;
   s.wa = o;   o += mode >= 1 ? SB * E * 4 : 0;
   s.wb = o;   o += mode >= 2 ? SB * E * 4 : 0;
@@ -129,24 +129,44 @@ __device__ __forceinline__ void ws_cp_arrive(uint32_t bar) {
 __device__ __forceinline__ void ws_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
+// 8 bf16 in a 16-byte word -> channels 0..3 / 4..7 as fp32 (a bf16 is the top half of an fp32)
+__device__ __forceinline__ float4 bf16x4_lo(const uint4& u) {
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+__device__ __forceinline__ float4 bf16x4_hi(const uint4& u) {
+  return make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u), __uint_as_float(u.w << 16),
+                     __uint_as_float(u.w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float4& a, const float4& b) {
+  return make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+}
 __device__ __forceinline__ float4 ws_prelu4(float4 a, float s) {
   return make_float4(prelu_f(a.x, s), prelu_f(a.y, s), prelu_f(a.z, s), prelu_f(a.w, s));
 }
 
 // LC = lanes that cover a row in 16-byte chunks (copy mapping); the reductions use L = LC/2 lanes per row, each
 // owning words gl and gl + L (LC = 4: one word per lane)
-template <int LC, int SB, int MODE>
+template <int LC, int SB, int MODE, bool BF16 = false>
 __global__ void __launch_bounds__(kWsThreads, 1) ws_kernel(const __grid_constant__ WsParams q, const WsSmem sm) {
+  // BF16 (MODE 0 only): feature rows are bf16 (x, out, z_out point to __nv_bfloat16 data, strides in elements);
+  // a 16-byte word then holds 8 channels, accumulation stays fp32
   extern __shared__ __align__(128) unsigned char smem[];
   const TileArgs& p = q.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = q.C, B = q.B, n_items = q.n_items;
-  const int words = C >> 2;
+  constexpr int ES = BF16 ? 2 : 4;                 // bytes per element
+  const int words = (C * ES) >> 4;                 // 16-byte words per row
   const int T = p.n_tiles;
   const int zrow = p.max_union;                    // index of the all-zero row of a stage
   const int EP = (p.max_entries + 3) & ~3;         // entry capacity of the per-sample scalar planes
   const int n_my = blockIdx.x < n_items ? (n_items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-  const uint32_t rowb = (uint32_t)C * 4u;
+  const uint32_t rowb = (uint32_t)C * (uint32_t)ES;
   const uint32_t sstride = (uint32_t)(zrow + 1) * rowb;
   const uint32_t dstride = (uint32_t)p.max_rows * rowb;
   const uint32_t smem_base = tile_smem_u32(smem);
@@ -219,21 +239,22 @@ __global__ void __launch_bounds__(kWsThreads, 1) ws_kernel(const __grid_constant
         // per-sample source pointers once per item; a row then costs one 32-bit multiply and, per sample, one
         // 64-bit add and the copy (n_nodes * C < 2^31 is checked by the host)
         const int32_t* us = reinterpret_cast<const int32_t*>(smem + sm.us + (j & 1) * usz);
-        const float* xp[SB];
+        const unsigned char* xp[SB];                         // byte pointers: fp32 or bf16 rows
 #pragma unroll
-        for (int s = 0; s < SB; ++s) xp[s] = q.x + (int64_t)(b0 + min(s, nb - 1)) * q.x_bstride + part * 4;
+        for (int s = 0; s < SB; ++s)
+          xp[s] = reinterpret_cast<const unsigned char*>(q.x) + ((int64_t)(b0 + min(s, nb - 1)) * q.x_bstride) * ES + part * 16;
         const uint32_t dst0 = st + sm.xs + part * 16;
         if (nb == SB) {
 #pragma unroll 4
           for (int u = g; u < da.w; u += NG) {
-            const uint32_t off = (uint32_t)us[u] * (uint32_t)C;
+            const uint32_t off = (uint32_t)us[u] * rowb;
             const uint32_t dst = dst0 + (uint32_t)u * rowb;
 #pragma unroll
             for (int s = 0; s < SB; ++s) ws_cp16(dst + s * sstride, xp[s] + off);
           }
         } else {
           for (int u = g; u < da.w; u += NG) {
-            const uint32_t off = (uint32_t)us[u] * (uint32_t)C;
+            const uint32_t off = (uint32_t)us[u] * rowb;
             const uint32_t dst = dst0 + (uint32_t)u * rowb;
 #pragma unroll
             for (int s = 0; s < SB; ++s)
@@ -291,7 +312,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) ws_kernel(const __grid_constant
   const uint32_t woff0 = live0 ? gl * 16 : 0, woff1 = live1 ? (gl + L) * 16 : 0;
   float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f), bv1 = bv0;         // MODE 0/1: bias;  MODE 2: att_src
   float4 cv0 = bv0, cv1 = bv0;                                      // MODE 2: att_dst
-  if (MODE <= 1 && q.bias) {
+  if (MODE <= 1 && q.bias && !BF16) {
     if (live0) bv0 = ldg4(q.bias + gl * 4);
     if (live1) bv1 = ldg4(q.bias + (gl + L) * 4);
   }
@@ -320,7 +341,59 @@ __global__ void __launch_bounds__(kWsThreads, 1) ws_kernel(const __grid_constant
 #pragma unroll
     for (int s = 0; s < SB; ++s) xb[s] = st + sm.xs + (uint32_t)min(s, nb - 1) * sstride;
 
-    if (MODE <= 2) {
+    if (BF16) {
+      // bf16 rows: a word = 8 channels; fp32 accumulators, bf16 results (round to nearest even)
+      for (int r = grp; r < nr; r += kGroups) {
+        const int le0 = re[r] - e0, le1 = re[r + 1] - e0;
+        const int64_t row = rid[r];
+        float4 acc[SB][WPL][2];
+#pragma unroll
+        for (int s = 0; s < SB; ++s)
+#pragma unroll
+          for (int wq = 0; wq < WPL; ++wq) acc[s][wq][0] = acc[s][wq][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int le = le0; le < le1; le += 2) {
+          const int4 e2 = *reinterpret_cast<const int4*>(en + le);
+          const uint32_t o0 = (uint32_t)e2.x * rowb, o1 = (uint32_t)e2.z * rowb;
+          const float w0 = __int_as_float(e2.y), w1 = __int_as_float(e2.w);
+#pragma unroll
+          for (int s = 0; s < SB; ++s) {
+#pragma unroll
+            for (int wq = 0; wq < WPL; ++wq) {
+              const uint32_t wo = wq ? woff1 : woff0;
+              const uint4 ua = *reinterpret_cast<const uint4*>(xb[s] + o0 + wo);
+              const uint4 ub = *reinterpret_cast<const uint4*>(xb[s] + o1 + wo);
+              fma4_packed(acc[s][wq][0], w0, bf16x4_lo(ua));
+              fma4_packed(acc[s][wq][1], w0, bf16x4_hi(ua));
+              fma4_packed(acc[s][wq][0], w1, bf16x4_lo(ub));
+              fma4_packed(acc[s][wq][1], w1, bf16x4_hi(ub));
+            }
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+          if (s >= nb) break;
+          const int64_t o = ((int64_t)(b0 + s) * q.out_bstride + row * C) * 2;     // byte offset
+#pragma unroll
+          for (int wq = 0; wq < WPL; ++wq) {
+            const int wd = wq ? gl + L : gl;
+            if (wq ? live1 : live0) {
+              float4 a0 = acc[s][wq][0], a1 = acc[s][wq][1];
+              if (q.bias) {
+                const float4 b0v = ldg4(q.bias + wd * 8), b1v = ldg4(q.bias + wd * 8 + 4);
+                a0 = make_float4(a0.x + b0v.x, a0.y + b0v.y, a0.z + b0v.z, a0.w + b0v.w);
+                a1 = make_float4(a1.x + b1v.x, a1.y + b1v.y, a1.z + b1v.z, a1.w + b1v.w);
+              }
+              if (q.z_out) *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(q.z_out) + o + wd * 16) = pack_bf16x8(a0, a1);
+              if (q.prelu_slope) {
+                a0 = ws_prelu4(a0, slope);
+                a1 = ws_prelu4(a1, slope);
+              }
+              *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(q.out) + o + wd * 16) = pack_bf16x8(a0, a1);
+            }
+          }
+        }
+      }
+    } else if (MODE <= 2) {
       for (int r = grp; r < nr; r += kGroups) {
         const int le0 = re[r] - e0, le1 = re[r + 1] - e0;             // even count: rows are padded to pairs
         const int64_t row = rid[r];
@@ -497,6 +570,45 @@ int ws_dispatch_l(const WsParams& q, cudaStream_t s, const char* what) {
   if (MODE != 3 && sb == 4) return ws_launch<LC, MODE == 3 ? 2 : 4, MODE>(q, s, what);
   if (sb >= 2) return ws_launch<LC, 2, MODE>(q, s, what);
   return ws_launch<LC, 1, MODE>(q, s, what);
+}
+
+// bf16 feature rows (MODE 0): words are 8 channels wide
+template <int LC, int SB>
+int ws_launch_bf16(WsParams q, cudaStream_t s, const char* what) {
+  const WsSmem sm = ws_smem(q.p, q.C, SB, 0, 2);
+  auto kern = ws_kernel<LC, SB, 0, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail_cuda(e, what);
+    attr_set = true;
+  }
+  const int64_t n_items = (int64_t)q.p.n_tiles * ceil_div(q.B, SB);
+  q.n_items = (int)n_items;
+  q.dbg = 0;
+  kern<<<(unsigned)std::min<int64_t>(n_items, kNumSMs), kWsThreads, sm.total, s>>>(q, sm);
+  GCL_CHECK_LAUNCH(what);
+  return GCL_OK;
+}
+
+template <int LC>
+int ws_dispatch_bf16_l(const WsParams& q, cudaStream_t s, const char* what) {
+  int sb = 2;
+  while (sb > 1 && (sb > q.B || ws_smem(q.p, q.C, sb, 0, 2).total > 227 * 1024)) sb >>= 1;
+  if (ws_smem(q.p, q.C, sb, 0, 2).total > 227 * 1024) {
+    set_error("%s: a tile (union %d rows of %d bf16 channels) does not fit the shared-memory ring", what, q.p.max_union, q.C);
+    return GCL_ERR_UNSUPPORTED;
+  }
+  if (sb == 2) return ws_launch_bf16<LC, 2>(q, s, what);
+  return ws_launch_bf16<LC, 1>(q, s, what);
+}
+
+inline int ws_dispatch_bf16(const WsParams& q, cudaStream_t s, const char* what) {
+  const int words = q.C / 8;
+  if (words <= 4) return ws_dispatch_bf16_l<4>(q, s, what);
+  if (words <= 8) return ws_dispatch_bf16_l<8>(q, s, what);
+  if (words <= 16) return ws_dispatch_bf16_l<16>(q, s, what);
+  return ws_dispatch_bf16_l<32>(q, s, what);
 }
 
 template <int MODE>

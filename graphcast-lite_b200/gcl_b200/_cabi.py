@@ -23,6 +23,7 @@ _PROTOS = {
     "gcl_spmm_f32": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "gcl_tile_plan_host": (c_int, [P, P, P, I64, I64, I64, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P]),
     "gcl_spmm_tiled_f32": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, I64, P, P, P, P]),
+    "gcl_spmm_tiled_bf16": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, I64, P, P, P, P]),
     "gcl_gat_fwd_tiled_f32": (c_int, [P] * 11 + [I64, I64, I64, I64, F32, P]),
     "gcl_gat_bwd_tiled_f32": (c_int, [P] * 14 + [I64, I64, I64, I64, F32, P]),
     "gcl_gat_ws_supported": (c_int, [P, P, I64, I64]),

@@ -86,6 +86,11 @@ class GCNConv(MessagePassing):
     def forward(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor] = None) -> Tensor:
         mode = CSR_LOOPS if self.add_self_loops else CSR_RAW
         g = GLOBAL_CACHE.get(edge_index, _num_nodes(x), mode, edge_weight)
+        if x.dtype == torch.bfloat16:
+            # optional bf16 feature rows (tolerance rel 2e-2): the dense transform runs in fp32 (3xTF32), the
+            # aggregation -- the HBM-bound part -- reads and writes bf16 rows
+            h = ops.linear(x.float(), self.lin.weight).to(torch.bfloat16)
+            return ops.aggregate(h, g, NORM_GCN if self.normalize else NORM_NONE, self.bias)
         h = ops.linear(x, self.lin.weight)
         return ops.aggregate(h, g, NORM_GCN if self.normalize else NORM_NONE, self.bias)
 

@@ -248,8 +248,63 @@ class _Aggregate(torch.autograd.Function):
         return dx, dbias, (dslope if ctx.has_slope and ctx.needs_input_grad[2] else None), None, None, None
 
 
+def spmm_bf16_raw(rowptr, col, w, x3, n_out, plan, bias=None, wkey=None):
+    """bf16 feature rows through the tiled engine (fp32 weights / bias / accumulation, bf16 result)."""
+    B, n_in, C = x3.shape
+    out = torch.empty((B, n_out, C), dtype=torch.bfloat16, device=x3.device)
+    ent = plan.entries(w, wkey)
+    with torch.cuda.device(x3.device):
+        nnz = int(col.numel())
+        nbytes = 2 * B * C * (n_in + n_out) + nnz * (8 if w is not None else 4) + 4 * (n_out + 1)
+        _call("gcl_spmm_tiled_bf16", plan.ref, _p(ent), _p(rowptr), _p(col), _p(w), _p(x3), _p(out), B, n_in, C,
+              n_in * C, n_out * C, _p(bias), None, None, _stream(), nbytes=nbytes, tag=f"N{n_out}xC{C}xB{B}xbf16")
+    return out
+
+
+class _AggregateBF16(torch.autograd.Function):
+    """_Aggregate for bf16 feature rows (north_star's optional storage format, tolerance rel 2e-2): x, out and the
+    gradients are bf16, weights / bias / accumulation fp32.  C must be a multiple of 8, <= 256 (no fallback)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, graph: CSRGraph, kind: int, rows_out=None):
+        if not x.is_cuda:
+            raise RuntimeError(f"gcl_b200: x is on {x.device}; the kernels are CUDA (sm_100a) only, no CPU fallback")
+        x3, squeeze = _as3(x.contiguous())
+        B, N, C = x3.shape
+        if N != graph.num_nodes:
+            raise ValueError(f"gcl_b200: x has {N} nodes, graph has {graph.num_nodes}")
+        if C % 8 or C > 256 or x3.data_ptr() % 16:
+            raise RuntimeError(f"gcl_b200: bf16 rows need 16-byte aligned rows of 8..256 channels (multiple of 8), got {C}")
+        n_out = N if rows_out is None else int(rows_out)
+        bias_c = _chk(bias, "bias") if bias is not None else None
+        w, _ = graph.weights(kind)
+        out = spmm_bf16_raw(graph.rowptr, graph.col, w, x3, n_out, graph.plan(False, n_out, N), bias_c, ("fwd", kind))
+        ctx.graph, ctx.kind, ctx.squeeze, ctx.has_bias = graph, kind, squeeze, bias is not None
+        return out.squeeze(0) if squeeze else out
+
+    @staticmethod
+    def backward(ctx, dout):
+        g = ctx.graph
+        d3, _ = _as3(dout.to(torch.bfloat16).contiguous())
+        dbias = dx = None
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            dbias = colsum_raw(d3.float().view(-1, d3.shape[-1]))
+        if ctx.needs_input_grad[0]:
+            _, wt = g.weights(ctx.kind)
+            dx = spmm_bf16_raw(g.rowptr_t, g.col_t, wt, d3, g.num_nodes, g.plan(True, g.num_nodes, d3.shape[1]),
+                               wkey=("bwd", ctx.kind))
+            if ctx.squeeze:
+                dx = dx.squeeze(0)
+        return dx, dbias, None, None, None
+
+
 def aggregate(x, graph: CSRGraph, kind: int, bias=None, prelu_slope=None, rows_out=None):
-    """rows_out = n: only receivers 0..n-1 are produced ([.., n, C]); their gradient flows back to all senders."""
+    """rows_out = n: only receivers 0..n-1 are produced ([.., n, C]); their gradient flows back to all senders.
+    bf16 x: the bf16 feature-row path (no fused PReLU)."""
+    if isinstance(x, torch.Tensor) and x.dtype == torch.bfloat16:
+        if prelu_slope is not None:
+            raise NotImplementedError("gcl_b200: the bf16 feature-row path has no fused PReLU epilogue")
+        return _AggregateBF16.apply(x, bias, graph, kind, rows_out)
     return _Aggregate.apply(x, bias, prelu_slope, graph, kind, rows_out)
 
 

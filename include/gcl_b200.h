@@ -156,6 +156,15 @@ int gcl_spmm_tiled_f32(const gcl_tile_plan* plan, const int32_t* ent, const int3
                        int64_t channels, int64_t x_bstride, int64_t out_bstride, const float* bias,
                        const float* prelu_slope, float* z_out, void* stream);
 
+/* bf16 feature rows (north_star: "128-bit vectorised loads of the ... bf16/fp32 feature rows", tolerance rel 2e-2):
+ * the same tiled engine with x / out / z_out holding bf16 ([B, N, C], strides in elements, C a multiple of 8, <= 256).
+ * Half the bytes cross HBM and L2; weights, bias and accumulation stay fp32, results are rounded to nearest even.
+ * Optional storage format of the aggregation layers, never the benchmark's headline dtype. */
+int gcl_spmm_tiled_bf16(const gcl_tile_plan* plan, const int32_t* ent, const int32_t* rowptr, const int32_t* col,
+                        const float* w, const void* x, void* out, int64_t batch, int64_t n_rows_in, int64_t channels,
+                        int64_t x_bstride, int64_t out_bstride, const float* bias, const float* prelu_slope,
+                        void* z_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K7  node-wise dense transform  y = act(x W^T + b)  (torch.nn.Linear in MLP, models.py:74-98, and the
  *   bias-free `lin` inside GCNConv/GATConv).  x [R, Cin], W [Cout, Cin], y [R, Cout].  Default engine:

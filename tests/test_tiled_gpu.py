@@ -164,3 +164,46 @@ def test_model_registers_order_hints_and_results_do_not_depend_on_them():
         finally:
             gg.ORDER_HINTS.update(saved)
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("C,B", [(64, 5), (128, 2), (96, 3), (256, 1), (8, 4)])
+def test_bf16_feature_rows(C, B):
+    """bf16 storage of the feature rows (north_star: rel 2e-2): the tiled engine with bf16 x / out and fp32
+    accumulation equals the fp32 kernel on the same (bf16-representable) inputs up to the final rounding to bf16;
+    forward, backward, heavy rows included; GCNConv on bf16 input vs the fp32 oracle within 2e-2."""
+    from gcl_b200 import ops
+    from gcl_b200.graph import CSR_LOOPS, NORM_GCN, CSRGraph
+    n = 3000
+    gen = torch.Generator().manual_seed(C)
+    ei = random_graph(n, 15000, seed=C + 1, isolated=20)
+    heavy_src = torch.randperm(n, generator=gen)[:400]
+    ei = torch.cat([ei, torch.stack([heavy_src, torch.full_like(heavy_src, 7)])], dim=1)
+    g = CSRGraph(ei.to(DEV), n, CSR_LOOPS)
+    assert g.plan(False).n_heavy == 1
+    x = torch.randn(B, n, C, generator=gen).to(torch.bfloat16)
+    bias = torch.randn(C, generator=gen)
+    go = torch.randn(B, n, C, generator=gen).to(torch.bfloat16)
+    xb = x.to(DEV).requires_grad_(True)
+    bb = bias.to(DEV).requires_grad_(True)
+    out = ops.aggregate(xb, g, NORM_GCN, bb)
+    assert out.dtype == torch.bfloat16
+    out.backward(go.to(DEV))
+    xf = x.float().to(DEV).requires_grad_(True)
+    bf = bias.to(DEV).requires_grad_(True)
+    ref = ops.aggregate(xf, g, NORM_GCN, bf)
+    ref.backward(go.float().to(DEV))
+    # only the final rounding to bf16 (2^-9 relative per element) separates the two
+    assert float((out.float() - ref).abs().max()) <= 2.0 ** -8 * float(ref.abs().max())
+    assert float((xb.grad.float() - xf.grad).abs().max()) <= 2.0 ** -8 * float(xf.grad.abs().max())
+    assert_close(bb.grad, bf.grad, 1e-5, "dbias")
+    assert torch.equal(ops.aggregate(xb.detach(), g, NORM_GCN, bb.detach()), out.detach())     # deterministic
+    if C <= 128:
+        import torch_geometric.nn as onn
+        import gcl_b200.nn as gnn
+        torch.manual_seed(C)
+        lo, lg = onn.GCNConv(C, C), gnn.GCNConv(C, C).to(DEV)
+        lg.load_state_dict(lo.state_dict())
+        y_ref = lo(x[0].float(), ei)
+        y = lg(x[0].to(DEV), ei.to(DEV))
+        assert y.dtype == torch.bfloat16
+        assert_close(y.float(), y_ref, 2e-2, "GCNConv on bf16 rows vs fp32 oracle")

@@ -94,6 +94,11 @@ def main():
                             err = float((got - ref).abs().max())
                             report(f"   tiled {hint_name} R<={mr} U<={mu}: tiles {pl.n_tiles} heavy {pl.n_heavy} "
                                    f"U/R {pl.union_per_row:.2f}", us, nbytes, f"maxdiff {err:.1e}")
+        if "bf16" in what and C % 8 == 0:
+            xh = [t.to(torch.bfloat16) for t in xs]
+            pl = g.plan(False)
+            us = timeit(lambda: ops.spmm_bf16_raw(g.rowptr, g.col, w, xh[it[0] % nrot], n, pl, bias, wkey="bf"))
+            report(f"spmm fwd {gname} bf16 rows (tiled)", us, nbytes // 2, f"{nbytes / us / 1e3 / PEAK:.2f} of HBM peak in fp32-equivalent bytes")
         if "gat" in what and gname == "mesh":
             z = torch.randn(B, n, C, device=dev, requires_grad=True)
             a_s = torch.randn(1, 1, C, device=dev, requires_grad=True)
