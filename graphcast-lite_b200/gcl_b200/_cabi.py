@@ -70,6 +70,12 @@ _PROTOS = {
     "gcl_forecast_metrics_workspace_bytes": (SZ, [I64, I64]),
     "gcl_forecast_metrics_f32": (c_int, [P, P, P, I64, I64, I64, P, SZ, P]),
     "gcl_resize_channels_f32": (c_int, [P, P, I64, I64, I64, P]),
+    "gcl_act_fwd_f32": (c_int, [P, P, I64, I32, P]),
+    "gcl_act_bwd_f32": (c_int, [P, P, P, I64, I32, P]),
+    "gcl_add_f32": (c_int, [P, P, P, I64, P]),
+    "gcl_layernorm_graph_workspace_bytes": (SZ, [I64]),
+    "gcl_layernorm_graph_fwd_f32": (c_int, [P, P, P, P, P, I64, I64, I64, F32, P, SZ, P]),
+    "gcl_layernorm_graph_bwd_f32": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, P, SZ, P]),
     "gcl_adam_f32": (c_int, [P, P, P, P, I64, F32, F32, F32, F32, F32, P, P]),
 }
 

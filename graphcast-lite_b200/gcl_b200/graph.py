@@ -263,3 +263,42 @@ class GraphCache:
 
 
 GLOBAL_CACHE = GraphCache()
+
+
+class EdgeOps:
+    """Gathers node rows onto edges and reduces edge rows onto nodes for a fixed edge list -- the index side of the
+    InteractionNet processor (models.py:213-219: x[senders], x[receivers], scatter(..., receivers, reduce='mean')).
+    Each direction is a CSR (one entry per edge row for the gathers, edges grouped by node for the reductions) with its
+    tile plan, so the work runs on the same deterministic SpMM kernels as the convolutions: a gather's backward is
+    the reduction over the same index and vice versa, no atomics."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+        _require_cuda(edge_index, "edge_index")
+        dev = edge_index.device
+        E, N = int(edge_index.shape[1]), int(num_nodes)
+        self.num_edges, self.num_nodes = E, N
+        i32 = torch.int32
+        ar = torch.arange(E + 1, dtype=i32, device=dev)
+        ones = None
+
+        def grouped(idx):                       # edges grouped by node idx[e], ascending edge id inside a node
+            order = torch.argsort(idx, stable=True)
+            cnt = torch.bincount(idx, minlength=N)
+            rp = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+            rp[1:] = torch.cumsum(cnt, 0)
+            return rp.to(i32).contiguous(), order.to(i32).contiguous(), cnt
+
+        src, dst = edge_index[0].contiguous(), edge_index[1].contiguous()
+        rp_s, col_s, _ = grouped(src)
+        rp_d, col_d, cnt_d = grouped(dst)
+        inv = 1.0 / cnt_d.clamp(min=1).to(torch.float32)
+        w_mean_csr = inv[dst[col_d.long()]].contiguous()          # weight per (node-grouped) entry
+        w_mean_edge = inv[dst].contiguous()                        # the same weights, one per edge row
+
+        def pack(rowptr, col, w, n_rows, n_cols):
+            plan = TilePlan(rowptr, col, int(col.numel()), n_rows, n_rows, n_cols, None, pad=2) if col.numel() else None
+            return (rowptr, col, w, n_rows, plan)
+        # gathers: edge row e <- node row idx[e];  reductions: node row i <- sum / mean of its edge rows
+        self.gather_src = (pack(ar, src.to(i32).contiguous(), ones, E, N), pack(rp_s, col_s, ones, N, E))
+        self.gather_dst = (pack(ar, dst.to(i32).contiguous(), ones, E, N), pack(rp_d, col_d, ones, N, E))
+        self.mean_dst = (pack(rp_d, col_d, w_mean_csr, N, E), pack(ar, dst.to(i32).contiguous(), w_mean_edge, E, N))

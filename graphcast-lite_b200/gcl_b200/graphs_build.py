@@ -126,6 +126,24 @@ def morton_order(xyz: np.ndarray) -> np.ndarray:
     return np.argsort(code, kind="stable").astype(np.int32)
 
 
+def mesh_edge_features(mesh_lat32: np.ndarray, mesh_lon32: np.ndarray, edge_index: np.ndarray) -> np.ndarray:
+    """[E, 4] float32 features of the mesh edges for the InteractionNet processor (create_graphs.py:37-91 through
+    utils.py:248-418): the sender's position minus the receiver's in the receiver's local frame (rotated so that the
+    receiver sits at longitude 0, latitude 0), and its length, both divided by the longest edge."""
+    from scipy.spatial.transform import Rotation
+    snd, rcv = edge_index[0], edge_index[1]
+    phi, theta = np.deg2rad(mesh_lon32), np.deg2rad(90 - mesh_lat32)              # utils.py:212-218 (float32 in, float32 out)
+    pos = np.stack([np.cos(phi) * np.sin(theta), np.sin(phi) * np.sin(theta), np.cos(theta)], axis=-1)
+    rot = Rotation.from_euler("zy", np.stack([-phi, -theta + np.pi / 2], axis=1)).as_matrix()     # utils.py:389-401
+    r_e = rot[rcv]
+    rel = np.einsum("bji,bi->bj", r_e, pos[snd]) - np.einsum("bji,bi->bj", r_e, pos[rcv])
+    dist = np.linalg.norm(rel, axis=-1, keepdims=True)
+    mx = dist.max()
+    if mx > 0:
+        dist, rel = dist / mx, rel / mx
+    return np.concatenate([dist, rel], axis=-1).astype(np.float32)
+
+
 # ------------------------------------------------------------------------------------------ searches (device)
 def _stream():
     return torch.cuda.current_stream().cuda_stream
@@ -195,9 +213,20 @@ class ModelGraphs:
         self.init_grid_features = torch.as_tensor(_static_features(glat.reshape(-1), glon.reshape(-1)), device=device)
         mlat, mlon = _mesh_lat_lon(verts)
         self.init_mesh_features = torch.as_tensor(_static_features(mlat, mlon), device=device)
+        self._mesh_lat_lon = (mlat, mlon)
+        self._edge_features = None
         # scheduling hints for the tiled aggregation kernels: mesh rows along a space-filling curve (grid rows are
         # already lat-major), so that a tile's rows share most of their neighbours
         from . import graph as _graph
         order = morton_order(verts)
         _graph.ORDER_HINTS[self.num_mesh] = order
         _graph.ORDER_HINTS[G + self.num_mesh] = np.concatenate([np.arange(G, dtype=np.int32), G + order]).astype(np.int32)
+
+    @property
+    def processing_edge_features(self) -> torch.Tensor:
+        """[E_mesh, 4] float32 on the device (built on first use: only the InteractionNet processor reads them)."""
+        if self._edge_features is None:
+            ei = self.processing_graph.cpu().numpy()
+            self._edge_features = torch.as_tensor(mesh_edge_features(*self._mesh_lat_lon, ei),
+                                                  device=self.processing_graph.device)
+        return self._edge_features

@@ -9,7 +9,8 @@ Same module tree and parameter names as /root/reference/src/models.py (MLP :54-1
   * Linear+bias+PReLU and aggregate+bias+PReLU are single kernels, graphs are device CSR built once,
     the encoder input is assembled by one kernel instead of zeros + 3 cats (models.py:776-806).
 
-Product graph, InteractionNet and regional meshes are out of scope.
+The InteractionNet processor of the v2 configs (models.py:166-285) is built from the same kernels (see
+InteractionNetLayer).  Product graph and regional meshes are out of scope.
 """
 from typing import Optional
 
@@ -19,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _cabi, ops
-from .graph import CSR_LOOPS, CSR_RAW, GLOBAL_CACHE, NORM_GCN, NORM_MEAN
+from .graph import CSR_LOOPS, CSR_RAW, GLOBAL_CACHE, NORM_GCN, NORM_MEAN, EdgeOps
 from .graphs_build import ModelGraphs
 from .nn import GATConv, GCNConv, LayerNorm, SimpleConv
 
@@ -73,6 +74,92 @@ class MLP(nn.Module):
         return X
 
 
+class ReLU(nn.Module):
+    """_get_activation("relu") (models.py:154-163) on the gcl kernels."""
+
+    def forward(self, x):
+        return ops.act(x, ops.ACT_RELU)
+
+
+class SiLU(nn.Module):
+    """_get_activation("swish" | "silu")."""
+
+    def forward(self, x):
+        return ops.act(x, ops.ACT_SILU)
+
+
+def _get_activation(name: str = "prelu") -> nn.Module:
+    if name in ("swish", "silu"):
+        return SiLU()
+    if name == "prelu":
+        return nn.PReLU()
+    if name == "relu":
+        return ReLU()
+    raise ValueError(f"Unknown activation: {name}")
+
+
+def _act_apply(m: nn.Module, x):
+    return ops.prelu(x, m.weight) if isinstance(m, nn.PReLU) else m(x)
+
+
+class InteractionNetLayer(nn.Module):
+    """One InteractionNetwork step (models.py:166-237), same parameters (edge_mlp.{0,2}, node_mlp.{0,2}, edge_norm,
+    node_norm), for B samples at once.  The first Linear of each MLP acts on a concatenation; it is evaluated as the
+    sum of its blocks (W [x_s | x_r | e] = W_s x_s + W_r x_r + W_e e), which moves the two node blocks in front of the
+    gather: two node-level GEMMs + two row gathers instead of a GEMM over [E, 3C]."""
+
+    def __init__(self, node_dim: int, edge_dim: int, hidden_dim: int, activation: str = "swish",
+                 use_layer_norm: bool = True):
+        super().__init__()
+        act = _get_activation(activation)
+        self.edge_mlp = nn.Sequential(nn.Linear(node_dim * 2 + edge_dim, hidden_dim), act, nn.Linear(hidden_dim, edge_dim))
+        self.node_mlp = nn.Sequential(nn.Linear(node_dim + edge_dim, hidden_dim), act, nn.Linear(hidden_dim, node_dim))
+        self.use_layer_norm = use_layer_norm
+        self.node_dim, self.edge_dim = node_dim, edge_dim
+        if use_layer_norm:
+            self.edge_norm = LayerNorm(edge_dim, mode="graph")
+            self.node_norm = LayerNorm(node_dim, mode="node")
+
+    def forward(self, x, eo: EdgeOps, edge_attr):
+        nd = self.node_dim
+        W1, b1 = self.edge_mlp[0].weight, self.edge_mlp[0].bias
+        ps = ops.spmm_fixed(ops.linear(x, W1[:, :nd]), *eo.gather_src)                 # (W_s x)[senders]
+        pr = ops.spmm_fixed(ops.linear(x, W1[:, nd:2 * nd]), *eo.gather_dst)           # (W_r x)[receivers]
+        h = ops.add(ops.add(ps, pr), ops.linear(edge_attr, W1[:, 2 * nd:], b1))
+        edge_update = ops.linear(_act_apply(self.edge_mlp[1], h), self.edge_mlp[2].weight, self.edge_mlp[2].bias)
+        aggregated = ops.spmm_fixed(edge_update, *eo.mean_dst)                           # scatter(..., reduce="mean")
+        Wn, bn = self.node_mlp[0].weight, self.node_mlp[0].bias
+        hn = ops.add(ops.linear(x, Wn[:, :nd], bn), ops.linear(aggregated, Wn[:, nd:]))
+        node_update = ops.linear(_act_apply(self.node_mlp[1], hn), self.node_mlp[2].weight, self.node_mlp[2].bias)
+        new_edge, new_x = ops.add(edge_attr, edge_update), ops.add(x, node_update)
+        if self.use_layer_norm:
+            new_edge, new_x = self.edge_norm(new_edge), self.node_norm(new_x)
+        return new_x, new_edge
+
+
+class InteractionNetProcessor(nn.Module):
+    """N unshared InteractionNet steps behind an edge-feature encoder (models.py:239-285)."""
+
+    def __init__(self, node_dim: int, raw_edge_dim: int, edge_latent_dim: int, hidden_dim: int, num_steps: int,
+                 activation: str = "swish", use_layer_norm: bool = True):
+        super().__init__()
+        self.edge_encoder = nn.Sequential(nn.Linear(raw_edge_dim, edge_latent_dim), _get_activation(activation))
+        self.steps = nn.ModuleList([InteractionNetLayer(node_dim, edge_latent_dim, hidden_dim, activation, use_layer_norm)
+                                    for _ in range(num_steps)])
+        self._edge_ops = None
+
+    def forward(self, x, edge_index, edge_attr_raw):
+        if self._edge_ops is None or self._edge_ops[0] is not edge_index:
+            self._edge_ops = (edge_index, EdgeOps(edge_index, x.size(-2)))
+        eo = self._edge_ops[1]
+        e = _act_apply(self.edge_encoder[1], ops.linear(edge_attr_raw, self.edge_encoder[0].weight, self.edge_encoder[0].bias))
+        if x.dim() == 3:                      # the encoded edge features are the same for every sample
+            e = e.unsqueeze(0).expand(x.size(0), -1, -1).contiguous()
+        for step in self.steps:
+            x, e = step(x, eo, e)
+        return x
+
+
 class SparseGATConv(GATConv):
     """models.py:112-151.  For B > 1 the pruning decision uses the batch-mean attention (over the global batch when
     data-parallel, so every replica prunes to the same graph)."""
@@ -106,12 +193,19 @@ class GraphLayer(nn.Module):
             self.output_dim = input_dim
             self.layers = SimpleConv(aggr="mean")
             return
+        if self.layer_type == "interaction_net":                    # models.py:376-398
+            self.output_dim = cfg["output_dim"]
+            if self.output_dim != input_dim:
+                raise ValueError(f"InteractionNet requires output_dim ({self.output_dim}) == input_dim ({input_dim})")
+            use_ln = cfg.get("use_layer_norm")
+            self.layers = InteractionNetProcessor(
+                node_dim=input_dim, raw_edge_dim=cfg.get("edge_feature_dim") or 4, edge_latent_dim=input_dim,
+                hidden_dim=input_dim, num_steps=cfg.get("num_message_passing_steps") or 4,
+                activation=cfg.get("activation") or "swish", use_layer_norm=True if use_ln is None else _truthy(use_ln))
+            return
         if self.layer_type not in ("conv_gcn", "conv_gat", "sparse_gat"):
             raise NotImplementedError(f"gcl_b200: layer type {self.layer_type!r} is out of scope (SURVEY.md 8)")
-        act = cfg.get("activation") or "prelu"
-        if act != "prelu":
-            raise NotImplementedError(f"gcl_b200: activation {act!r} (v2 configs) is out of scope")
-        self.activation = nn.PReLU()
+        self.activation = _get_activation(cfg.get("activation") or "prelu")
         self.output_dim = cfg["output_dim"]
         self.layers = nn.ModuleList()
         hid = list(cfg.get("hidden_dims") or [])
@@ -136,6 +230,11 @@ class GraphLayer(nn.Module):
         rows).  Honoured when the last module is a GCNConv -- its aggregation then produces just those receivers."""
         if self.layer_type == "simple_conv":
             return self.layers(x=X, edge_index=edge_index)
+        if self.layer_type == "interaction_net":                     # models.py:435-439
+            edge_attr = kwargs.get("edge_attr")
+            if edge_attr is None:
+                raise ValueError("InteractionNet requires edge_attr (edge features)")
+            return self.layers(X, edge_index, edge_attr)
         if self.layer_type == "sparse_gat":
             for layer in self.layers:
                 if type(layer) is SparseGATConv:
@@ -179,7 +278,7 @@ class GraphLayer(nn.Module):
                 X = ops.prelu(X, m.weight)
                 i += 1
             else:
-                X = m(X)
+                X = m(X)                      # ReLU / SiLU (v2 configs), LayerNorm
                 i += 1
         return X
 
@@ -253,6 +352,10 @@ class WeatherPrediction(nn.Module):
         self.init_grid_features, self.init_mesh_features = g.init_grid_features, g.init_mesh_features
         pipe = cfg["pipeline"]
         self.using_sparse_gat = pipe["processor"]["gcn"]["layer_type"] == "sparse_gat"
+        self.using_interaction_net = pipe["processor"]["gcn"]["layer_type"] == "interaction_net"
+        # 4-d mesh edge features (create_graphs.py:37-91); a buffer in the reference (models.py:558), so it is one here
+        self.register_buffer("_processing_edge_features",
+                             g.processing_edge_features.clone() if self.using_interaction_net else None)
         self.encoder = Model(pipe["encoder"], self.total_feature_size + self.init_grid_features.shape[1])
         self.processor = Model(pipe["processor"], self.encoder.output_dim)
         self.decoder = Model(pipe["decoder"], self.processor.output_dim)
@@ -261,7 +364,9 @@ class WeatherPrediction(nn.Module):
         self.to(self.device)
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        sd = {k: v for k, v in state_dict.items() if k != "_processing_edge_features"}
+        # the reference registers the edge features as a buffer for every model (models.py:558); here only the
+        # InteractionNet models keep them
+        sd = {k: v for k, v in state_dict.items() if k != "_processing_edge_features" or self.using_interaction_net}
         return super().load_state_dict(sd, strict=strict, **kw)
 
     def forward(self, X: torch.Tensor, attention_threshold=0.0, **kwargs):
@@ -282,6 +387,9 @@ class WeatherPrediction(nn.Module):
             proc, new_ei = self.processor(X=mesh_lat, edge_index=self.processing_graph,
                                           attention_threshold=attention_threshold, **kwargs)
             self.processing_graph = new_ei           # models.py:846
+        elif self.using_interaction_net:                              # models.py:847-853
+            proc = self.processor(X=mesh_lat, edge_index=self.processing_graph,
+                                  attention_threshold=attention_threshold, edge_attr=self._processing_edge_features)
         else:
             proc = self.processor(X=mesh_lat, edge_index=self.processing_graph,
                                   attention_threshold=attention_threshold)

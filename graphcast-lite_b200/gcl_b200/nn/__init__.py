@@ -182,9 +182,9 @@ class SimpleConv(MessagePassing):
 
 
 class LayerNorm(torch.nn.Module):
-    """torch_geometric.nn.LayerNorm (models.py:103,370).  mode='node' -- the mode of every BASELINE
-    config -- runs the fused kernel; mode='graph' (whole-sample statistics) is composed from torch
-    reductions around it and is not on the measured path."""
+    """torch_geometric.nn.LayerNorm (models.py:103,370; InteractionNet's edge_norm :201).  mode='node' -- the mode of
+    every BASELINE config -- normalises each row; mode='graph' normalises by the statistics of the whole sample
+    ([N, C], or every [N, C] slice of a [B, N, C] batch).  Both are kernels (gcl_layernorm_*), CUDA only."""
 
     def __init__(self, in_channels: int, eps: float = 1e-5, affine: bool = True, mode: str = "graph"):
         super().__init__()
@@ -208,14 +208,7 @@ class LayerNorm(torch.nn.Module):
             return ops.layer_norm(x, self.weight, self.bias, self.eps)
         if batch is not None:
             raise NotImplementedError("gcl_b200.LayerNorm(mode='graph'): `batch` vectors are not used by graphcast-lite")
-        if not x.is_cuda:
-            raise RuntimeError("gcl_b200.LayerNorm: CUDA tensors only; no CPU fallback")
-        dims = (-2, -1)
-        xc = x - x.mean(dim=dims, keepdim=True)
-        out = xc / (xc.pow(2).mean(dim=dims, keepdim=True).sqrt() + self.eps)
-        if self.affine:
-            out = out * self.weight + self.bias
-        return out
+        return ops.layer_norm_graph(x, self.weight, self.bias, self.eps)
 
     def __repr__(self):
         return f"{type(self).__name__}({self.in_channels}, affine={self.affine}, mode={self.mode})"

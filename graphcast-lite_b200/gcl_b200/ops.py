@@ -732,6 +732,130 @@ def resize_channels(x, c: int):
     return _ResizeChannels.apply(x, c)
 
 
+ACT_RELU, ACT_SILU = 1, 2
+
+
+class _Act(torch.autograd.Function):
+    """ReLU / SiLU of _get_activation (models.py:154-163)."""
+
+    @staticmethod
+    def forward(ctx, x, kind):
+        xc = _chk(x, "x")
+        y = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            _call("gcl_act_fwd_f32", _p(xc), _p(y), xc.numel(), int(kind), _stream(), nbytes=8 * xc.numel())
+        ctx.save_for_backward(xc)
+        ctx.kind = int(kind)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        d = _chk(dy, "grad_out")
+        dx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _call("gcl_act_bwd_f32", _p(d), _p(x), _p(dx), x.numel(), ctx.kind, _stream(), nbytes=12 * x.numel())
+        return dx, None
+
+
+def act(x, kind: int):
+    return _Act.apply(x, kind)
+
+
+class _Add(torch.autograd.Function):
+    """a + b (residual connections, models.py:226-227); the gradient passes through unchanged."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ac, bc = _chk(a, "a"), _chk(b, "b")
+        if ac.shape != bc.shape:
+            raise ValueError(f"gcl_b200: add got {tuple(ac.shape)} and {tuple(bc.shape)}")
+        y = torch.empty_like(ac)
+        with torch.cuda.device(ac.device):
+            _call("gcl_add_f32", _p(ac), _p(bc), _p(y), ac.numel(), _stream(), nbytes=12 * ac.numel())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
+class _LayerNormGraph(torch.autograd.Function):
+    """torch_geometric LayerNorm(mode='graph') without a batch vector: statistics over all elements of a sample
+    ([N, C], or each [N, C] slice of [B, N, C]); y = (x - mean) / (std + eps) * weight + bias."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        xc = _chk(x, "x")
+        x3, squeeze = _as3(xc)
+        B, N, C = x3.shape
+        g = _chk(gamma, "weight") if gamma is not None else None
+        b = _chk(beta, "bias") if beta is not None else None
+        y = torch.empty_like(x3)
+        stats = torch.empty((B, 3), dtype=torch.float32, device=xc.device)
+        lib = _cabi.load()
+        nb = lib.gcl_layernorm_graph_workspace_bytes(B)
+        ws = _ws(nb, xc.device)
+        with torch.cuda.device(xc.device):
+            _call("gcl_layernorm_graph_fwd_f32", _p(x3), _p(g), _p(b), _p(y), _p(stats), B, N * C, C, float(eps), _p(ws), nb,
+                  _stream(), nbytes=12 * x3.numel(), tag=f"B{B}xN{N}xC{C}")
+        ctx.save_for_backward(x3, g, stats)
+        ctx.affine, ctx.squeeze = gamma is not None, squeeze
+        return y.squeeze(0) if squeeze else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x3, g, stats = ctx.saved_tensors
+        B, N, C = x3.shape
+        d3, _ = _as3(_chk(dy, "grad_out"))
+        dx = torch.empty_like(x3)
+        t = torch.empty_like(x3) if ctx.affine else None
+        coef = torch.empty((B, 2), dtype=torch.float32, device=x3.device)
+        lib = _cabi.load()
+        nb = lib.gcl_layernorm_graph_workspace_bytes(B)
+        ws = _ws(nb, x3.device)
+        with torch.cuda.device(x3.device):
+            _call("gcl_layernorm_graph_bwd_f32", _p(d3), _p(x3), _p(g), _p(stats), _p(dx), _p(t), _p(coef), B, N * C, C,
+                  _p(ws), nb, _stream(), nbytes=16 * x3.numel(), tag=f"B{B}xN{N}xC{C}")
+        dg = db = None
+        if ctx.affine:
+            dg = colsum_raw(t.view(-1, C))
+            db = colsum_raw(d3.reshape(-1, C))
+        return (dx.squeeze(0) if ctx.squeeze else dx), dg, db, None
+
+
+def layer_norm_graph(x, weight, bias, eps=1e-5):
+    return _LayerNormGraph.apply(x, weight, bias, eps)
+
+
+class _SpmmFixed(torch.autograd.Function):
+    """out = A x with a fixed sparse A given as CSR (+ optional tile plan) and A^T for the backward: the building block of
+    the edge gathers / scatters of the InteractionNet processor.  x [B, n_in, C] -> [B, n_out, C]."""
+
+    @staticmethod
+    def forward(ctx, x, fwd, bwd):
+        x3, squeeze = _as3(_chk(x, "x"))
+        rowptr, col, w, n_out, plan = fwd
+        out, _ = spmm_raw(rowptr, col, w, x3, n_out, plan=plan if _tileable(x3.shape[-1]) else None, wkey=("fixed", id(w)))
+        ctx.bwd, ctx.squeeze = bwd, squeeze
+        return out.squeeze(0) if squeeze else out
+
+    @staticmethod
+    def backward(ctx, dout):
+        d3, _ = _as3(_chk(dout, "grad_out"))
+        rowptr, col, w, n_out, plan = ctx.bwd
+        dx, _ = spmm_raw(rowptr, col, w, d3, n_out, plan=plan if _tileable(d3.shape[-1]) else None, wkey=("fixed", id(w)))
+        return (dx.squeeze(0) if ctx.squeeze else dx), None, None
+
+
+def spmm_fixed(x, fwd, bwd):
+    return _SpmmFixed.apply(x, fwd, bwd)
+
+
 def edge_prune(ei_pyg: torch.Tensor, alpha_pyg: torch.Tensor, threshold: float) -> torch.Tensor:
     """SparseGATConv pruning (models.py:140-149): edges with alpha >= threshold, order preserved."""
     if not ei_pyg.is_cuda or not alpha_pyg.is_cuda:

@@ -69,6 +69,18 @@ WORKLOADS = {
             "decoder": {"mlp": _mlp([128, 64], 64, False), "gcn": _gcn("conv_gcn", [64, 64], 19)}}},
 }
 
+# The InteractionNet family: experiments/wb2_512x256_19f_ar_v2/config.json -- 256-wide, swish,
+# 12 unshared message-passing steps with 4-d mesh edge features.  Not a BASELINE.json config; kept beside them for the
+# parity tests and an optional bench line (`bench.py --workload wb2_512x256_19f_ar_v2`).
+WORKLOADS["wb2_512x256_19f_ar_v2"] = {
+    "nlat": 256, "nlon": 512, "max_ar_steps": 4, "learning_rate": 3e-4,
+    "graph": _graph([4, 6], 0.6), "data": _data(19, 2, 1),
+    "pipeline": {
+        "encoder": {"mlp": _mlp([256, 256], 256, True), "gcn": dict(_gcn("conv_gcn", [256, 256], 256), activation="swish")},
+        "processor": {"gcn": {"layer_type": "interaction_net", "output_dim": 256, "activation": "swish",
+                              "use_layer_norm": True, "num_message_passing_steps": 12, "edge_feature_dim": 4}},
+        "decoder": {"mlp": _mlp([256, 128], 128, False), "gcn": dict(_gcn("conv_gcn", [128, 128], 19), activation="swish")}}}
+
 # name -> expected trainable parameter count (209 882 pinned by README_RU.MD:141)
 PARAM_COUNTS = {"baseline": 53784, "attention": 54168, "sparse_attention": 20625,
                 "wb2_64x32_ar_15f_4obs_4pred": 95782, "wb2_512x256_19f_ar": 209882}

@@ -402,6 +402,29 @@ int gcl_ar_step_bwd_f32(const float* g_loss, const float* dloss, const float* d_
                         int residual, float* d_delta, float* d_state, int64_t batch, int64_t n_grid, int64_t obs,
                         int64_t c, void* stream);
 /* ------------------------------------------------------------------------------------------------
+ * f3  InteractionNet processor (models.py:166-285) and the v2 configs: what they need beyond the kernels above.
+ *   activations of _get_activation (models.py:154-163) other than PReLU: ReLU, SiLU ("swish");
+ *   torch_geometric LayerNorm(mode="graph") (edge_norm, models.py:201): per sample,
+ *     y = (x - mean) / (std(unbiased=False) + eps) * gamma[c] + beta[c], statistics over ALL elems_per_sample
+ *     elements (float64 accumulation, fixed order); stats float [batch][3] = (mean, 1 / (std + eps), std) is saved
+ *     for the backward, which returns dx, coef (scratch float [batch][2]) and t_out = dy * xhat (nullable) whose
+ *     column sums are d gamma (d beta = column sums of dy; both with gcl_colsum_f32);
+ *   gcl_add_f32: the residual connections (models.py:226-227).
+ */
+#define GCL_ACT_RELU 1
+#define GCL_ACT_SILU 2
+int gcl_act_fwd_f32(const float* x, float* y, int64_t n, int kind, void* stream);
+int gcl_act_bwd_f32(const float* dy, const float* x, float* dx, int64_t n, int kind, void* stream);
+int gcl_add_f32(const float* a, const float* b, float* y, int64_t n, void* stream);
+size_t gcl_layernorm_graph_workspace_bytes(int64_t batch);
+int gcl_layernorm_graph_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* stats,
+                                int64_t batch, int64_t elems_per_sample, int64_t c, float eps, void* workspace,
+                                size_t workspace_bytes, void* stream);
+int gcl_layernorm_graph_bwd_f32(const float* dy, const float* x, const float* gamma, const float* stats, float* dx,
+                                float* t_out, float* coef, int64_t batch, int64_t elems_per_sample, int64_t c,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * f2  input pipeline, device side.  TimeseriesChunkDataset.__getitem__ (src/data/dataloader_chunked.py:179-223)
  *   converts, normalises and transposes every window on CPU workers; here the host only stages RAW windows and one
  *   kernel produces both model tensors for the whole batch:

@@ -139,6 +139,27 @@ def node_features(lat_f32: np.ndarray, lon_f32: np.ndarray) -> np.ndarray:
     return np.stack(cols, axis=-1).astype(np.float32)
 
 
+def mesh_edge_features(mlat: np.ndarray, mlon: np.ndarray, edge_index: np.ndarray) -> np.ndarray:
+    """create_graphs.py:37-91 (_compute_mesh_edge_features): relative position of the sender in the receiver's
+    local coordinates (utils.py:248-343, rotation matrices :345-418) and its norm, normalised by the largest norm."""
+    senders, receivers = edge_index[0], edge_index[1]
+    phi = np.deg2rad(mlon)
+    theta = np.deg2rad(90 - mlat)
+    node_pos = np.stack((np.cos(phi) * np.sin(theta), np.sin(phi) * np.sin(theta), np.cos(theta)), axis=-1)
+    azimuthal_rotation = -phi
+    polar_rotation = -theta + np.pi / 2
+    mats = Rotation.from_euler("zy", np.stack([azimuthal_rotation, polar_rotation], axis=1)).as_matrix()
+    edge_mats = mats[receivers]
+    recv_rot = np.einsum("bji,bi->bj", edge_mats, node_pos[receivers])
+    send_rot = np.einsum("bji,bi->bj", edge_mats, node_pos[senders])
+    relative_position = send_rot - recv_rot
+    d = np.linalg.norm(relative_position, axis=-1, keepdims=True)
+    max_dist = d.max()
+    if max_dist > 0:
+        d, relative_position = d / max_dist, relative_position / max_dist
+    return np.concatenate([d, relative_position], axis=-1).astype(np.float32)
+
+
 def build_graphs(nlat: int, nlon: int, mesh_levels, radius_factor: float):
     """Everything WeatherPrediction.__init__ builds (models.py:507-570) for a regular grid."""
     lat64 = np.linspace(-90, 90, nlat)                        # main.py:45-56 (float64)
@@ -159,4 +180,5 @@ def build_graphs(nlat: int, nlon: int, mesh_levels, radius_factor: float):
                                     glon.reshape(-1).astype(np.float32)),
         "mesh_feats": node_features(mlat, mlon),
     }
+    out["mesh_edge_feats"] = mesh_edge_features(mlat, mlon, out["mesh"])
     return out

@@ -7,7 +7,8 @@ be checked (and timed as the CPU baseline) on the GPU box, where /root/reference
   SparseGATConv      /root/reference/src/models.py:112-151
   GraphLayer         /root/reference/src/models.py:289-440   (SimpleConv / ConvGCN / GATConv / SparseGATConv)
   Model              /root/reference/src/models.py:443-473
-  WeatherPrediction  /root/reference/src/models.py:476-601, 776-874  (no product graph, no InteractionNet)
+  InteractionNet     /root/reference/src/models.py:166-285
+  WeatherPrediction  /root/reference/src/models.py:476-601, 776-874  (no product graph)
   weighted MSE + AR rollout of one training step   /root/reference/src/train.py:85-102, 160-233
 
 The conv / norm arithmetic comes from oracle/pyg_shim (restated torch_geometric 2.5.3).  Module and
@@ -70,6 +71,52 @@ class SparseGATConv(GATConv):
         return out, (edge_index, att)
 
 
+_ACTS = {"prelu": nn.PReLU, "relu": nn.ReLU, "silu": nn.SiLU, "swish": nn.SiLU}
+
+
+class InteractionNetLayer(nn.Module):
+    """models.py:166-237: edge MLP on [x_s | x_r | e], scatter-mean onto receivers, node MLP on [x | agg], residuals,
+    LayerNorm(graph) on the edges and LayerNorm(node) on the nodes."""
+
+    def __init__(self, node_dim, edge_dim, hidden_dim, activation="swish", use_layer_norm=True):
+        super().__init__()
+        act = _ACTS[activation]()
+        self.edge_mlp = nn.Sequential(nn.Linear(node_dim * 2 + edge_dim, hidden_dim), act, nn.Linear(hidden_dim, edge_dim))
+        self.node_mlp = nn.Sequential(nn.Linear(node_dim + edge_dim, hidden_dim), act, nn.Linear(hidden_dim, node_dim))
+        self.use_layer_norm = use_layer_norm
+        if use_layer_norm:
+            self.edge_norm = LayerNorm(edge_dim, mode="graph")
+            self.node_norm = LayerNorm(node_dim, mode="node")
+
+    def forward(self, x, edge_index, edge_attr):
+        from torch_geometric.utils import scatter
+        senders, receivers = edge_index[0], edge_index[1]
+        edge_update = self.edge_mlp(torch.cat([x[senders], x[receivers], edge_attr], dim=-1))
+        aggregated = scatter(edge_update, receivers, dim=0, dim_size=x.size(0), reduce="mean")
+        node_update = self.node_mlp(torch.cat([x, aggregated], dim=-1))
+        new_edge_attr, new_x = edge_attr + edge_update, x + node_update
+        if self.use_layer_norm:
+            new_edge_attr, new_x = self.edge_norm(new_edge_attr), self.node_norm(new_x)
+        return new_x, new_edge_attr
+
+
+class InteractionNetProcessor(nn.Module):
+    """models.py:239-285."""
+
+    def __init__(self, node_dim, raw_edge_dim, edge_latent_dim, hidden_dim, num_steps, activation="swish",
+                 use_layer_norm=True):
+        super().__init__()
+        self.edge_encoder = nn.Sequential(nn.Linear(raw_edge_dim, edge_latent_dim), _ACTS[activation]())
+        self.steps = nn.ModuleList([InteractionNetLayer(node_dim, edge_latent_dim, hidden_dim, activation, use_layer_norm)
+                                    for _ in range(num_steps)])
+
+    def forward(self, x, edge_index, edge_attr_raw):
+        edge_attr = self.edge_encoder(edge_attr_raw)
+        for step in self.steps:
+            x, edge_attr = step(x, edge_index, edge_attr)
+        return x
+
+
 class GraphLayer(nn.Module):
     def __init__(self, cfg: dict, input_dim: int):
         super().__init__()
@@ -78,9 +125,17 @@ class GraphLayer(nn.Module):
             self.output_dim = input_dim
             self.layers = SimpleConv(aggr="mean")
             return
+        if self.layer_type == "interaction_net":                    # models.py:376-398
+            self.output_dim = cfg["output_dim"]
+            assert self.output_dim == input_dim
+            use_ln = cfg.get("use_layer_norm")
+            self.layers = InteractionNetProcessor(input_dim, cfg.get("edge_feature_dim") or 4, input_dim, input_dim,
+                                                  cfg.get("num_message_passing_steps") or 4,
+                                                  cfg.get("activation") or "swish",
+                                                  True if use_ln is None else _truthy(use_ln))
+            return
         assert self.layer_type in ("conv_gcn", "conv_gat", "sparse_gat"), self.layer_type
-        act = cfg.get("activation") or "prelu"
-        self.activation = {"prelu": nn.PReLU, "relu": nn.ReLU, "silu": nn.SiLU, "swish": nn.SiLU}[act]()
+        self.activation = _ACTS[cfg.get("activation") or "prelu"]()
         self.output_dim = cfg["output_dim"]
         self.layers = nn.ModuleList()
         hid = cfg.get("hidden_dims") or []
@@ -103,6 +158,8 @@ class GraphLayer(nn.Module):
     def forward(self, X, edge_index, attention_threshold=0.0, **kwargs):
         if self.layer_type == "simple_conv":
             return self.layers(x=X, edge_index=edge_index)
+        if self.layer_type == "interaction_net":
+            return self.layers(x=X, edge_index=edge_index, edge_attr_raw=kwargs["edge_attr"])
         if self.layer_type == "sparse_gat":
             for layer in self.layers:
                 if type(layer) is SparseGATConv:
@@ -147,6 +204,9 @@ class WeatherPrediction(nn.Module):
         self.init_mesh_features = torch.as_tensor(g["mesh_feats"])
         pipe = cfg["pipeline"]
         self.using_sparse_gat = pipe["processor"]["gcn"]["layer_type"] == "sparse_gat"
+        self.using_interaction_net = pipe["processor"]["gcn"]["layer_type"] == "interaction_net"
+        self.register_buffer("_processing_edge_features",
+                             torch.as_tensor(g["mesh_edge_feats"]) if self.using_interaction_net else None)
         self.encoder = Model(pipe["encoder"], self.total_feature_size + 6)
         self.processor = Model(pipe["processor"], self.encoder.output_dim)
         self.decoder = Model(pipe["decoder"], self.processor.output_dim)
@@ -160,6 +220,9 @@ class WeatherPrediction(nn.Module):
             proc, new_ei = self.processor(X=mesh_lat, edge_index=self.processing_graph,
                                           attention_threshold=attention_threshold, **kwargs)
             self.processing_graph = new_ei
+        elif self.using_interaction_net:
+            proc = self.processor(X=mesh_lat, edge_index=self.processing_graph, attention_threshold=attention_threshold,
+                                  edge_attr=self._processing_edge_features)
         else:
             proc = self.processor(X=mesh_lat, edge_index=self.processing_graph,
                                   attention_threshold=attention_threshold)

@@ -254,3 +254,37 @@ def test_oracle_loss_matches_the_reference_functions():
         b = ns["weighted_mse_loss"](pred, tgt, lw_ref, **kw)
         assert torch.equal(a, b), kw
     assert torch.equal(om.weighted_mse(pred, tgt), ns["weighted_mse_loss"](pred, tgt))
+
+
+def _small_inet_cfg(width=32, steps=2, act="swish"):
+    from gcl_b200.workloads import get_workload
+    cfg = get_workload("wb2_512x256_19f_ar_v2")
+    cfg["graph"]["mesh_levels"], cfg["graph"]["grid2mesh_radius_query"] = [1, 3], 0.6
+    for part in ("encoder", "decoder"):
+        m, g = cfg["pipeline"][part]["mlp"], cfg["pipeline"][part]["gcn"]
+        m["mlp_hidden_dims"] = [width] * len(m["mlp_hidden_dims"])
+        g["hidden_dims"] = [width] * len(g["hidden_dims"])
+        g["activation"] = act
+    cfg["pipeline"]["encoder"]["mlp"]["output_dim"] = cfg["pipeline"]["encoder"]["gcn"]["output_dim"] = width
+    cfg["pipeline"]["processor"]["gcn"].update(output_dim=width, num_message_passing_steps=steps, activation=act)
+    cfg["pipeline"]["decoder"]["mlp"]["output_dim"] = width
+    return cfg
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("act", ["swish", "relu"])
+def test_interaction_net_glue_matches_unmodified_reference(act):
+    """f3: the oracle's InteractionNet processor, the 4-d mesh edge features and the v2 activations against the
+    UNMODIFIED reference WeatherPrediction (models.py:166-285, create_graphs.py:37-91) on the shims: bit-exact."""
+    from oracle import graphs as og, model as om
+    cfg = _small_inet_cfg(act=act)
+    ref = _reference_model(cfg, 16, 32)
+    g = og.build_graphs(16, 32, [1, 3], 0.6)
+    assert np.array_equal(ref._processing_edge_features.numpy(), g["mesh_edge_feats"])
+    mine = om.WeatherPrediction(cfg, 16, 32, graphs=g)
+    mine.load_state_dict(ref.state_dict())
+    assert sorted(mine.state_dict()) == sorted(ref.state_dict())
+    X = torch.randn(1, 512, 38, generator=torch.Generator().manual_seed(0))
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = ref(X=X, attention_threshold=0.0)
+    assert torch.equal(a, mine(X=X, attention_threshold=0.0))
