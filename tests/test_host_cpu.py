@@ -64,7 +64,9 @@ def test_workload_table_matches_reference_configs():
         for part in ("encoder", "processor", "decoder"):
             rg, wg = cfg["pipeline"][part]["gcn"], w["pipeline"][part]["gcn"]
             assert rg["layer_type"] == wg["layer_type"]
-            assert (rg.get("hidden_dims") or []) == wg["hidden_dims"]
+            assert (rg.get("hidden_dims") or []) == (wg.get("hidden_dims") or [])
+            for k in ("activation", "num_message_passing_steps", "edge_feature_dim"):      # v2 / InteractionNet keys
+                assert (rg.get(k) or {"activation": "prelu"}.get(k)) == (wg.get(k) or {"activation": "prelu"}.get(k)), (name, part, k)
             assert rg.get("output_dim") == wg["output_dim"]
             assert bool(norm(rg.get("use_layer_norm", False))) == bool(wg["use_layer_norm"])
             rm, wm = cfg["pipeline"][part].get("mlp"), w["pipeline"][part].get("mlp")
