@@ -958,6 +958,311 @@ __global__ void __launch_bounds__(kLtThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Weights-stationary variant for the wide layers (64 < N <= 128, K <= 128): C^T = W X^T.
+//
+// In the kernel above the resident W (hi + lo) of a 128 -> 128 layer takes 128 KB of shared memory, so it has to
+// run column-split (n_split = 2): every A tile goes through shared memory twice (TMA write, converter read + write,
+// MMA operand reads, in both CTAs of a pair) and ncu shows the shared-memory pipe, not HBM, as the bound (~1.1 MB
+// of shared-memory traffic per 128 output rows at 128 B/clk).  Here the roles of the operands are swapped:
+//   * W is the M-side operand and lives in TENSOR MEMORY (tcgen05.mma with the A operand in TMEM): lane = output
+//     channel, 128 columns of hi and 128 of lo.  It costs no shared memory and no shared-memory bandwidth;
+//   * the activations are the N-side operand: [64 rows x 32 floats] slabs, hi (raw, truncated by the tensor core)
+//     and lo adjacent in one 16 KB stage, so W_hi x [X_hi | X_lo] is ONE MMA of N = 128 (main | correction
+//     accumulator columns) followed by W_lo x X_hi (N = 64) into the correction columns -- the same three products;
+//   * the accumulator is the transposed tile [channel lane][row column]; the epilogue thread of channel c writes
+//     its 64 rows into the swizzled output slabs with 4-byte stores (32 consecutive channels of one row = 32
+//     different banks) and the tile leaves by TMA tensor stores as before.
+// Shared-memory traffic per 64 rows: 32 KB TMA write, 64 KB converter, 96 KB MMA operand reads, 64 KB output
+// = 256 KB (1.0 us at 128 B/clk) against 1.45 us of HBM time for the tile: HBM is the bound again.
+// TMEM: columns 0..127 W_hi, 128..255 W_lo, 256..383 and 384..511 two accumulators (main 64 | correction 64).
+constexpr int kTsRows = 64;
+constexpr int kTsSlab = kTsRows * 128;          // [64 rows x 32 fp32], 8 KB
+constexpr int kTsStage = 2 * kTsSlab;           // hi | lo
+constexpr int kTsWCols = 128, kTsAcc0 = 2 * kTsWCols, kTsAccCols = 2 * kTsRows;
+
+// D[tmem] (+)= A[tmem] * B[smem]: the M-side operand is read from tensor memory (lane = row, one tf32 per column)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// thread i of the warp writes 16 consecutive columns of TMEM lane (base lane + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+
+// roles (17 warps): 0-7 epilogue (warp w: TMEM lanes = channels 32 (w % 4).., rows 32 (w / 4)..), 8 MMA issue +
+// TMEM allocation, 9 TMA producer, 10-13 converters, 14-16 MMA issue.  Four MMA-issuing warps, tile t belongs to
+// warp t % 4: with 64-row tiles a single issuing warp -- ~60 dependent uniform-datapath instructions per 16 KB
+// stage -- was the critical path (ncu: that warp never idle, tensor pipe 47 %, converters waiting for data).  A
+// tile's MMAs all come from one thread, so their order and the commit that follows them are unaffected.
+constexpr int kTsMmaWarps = 4;
+constexpr int kTsWarps = kLtEpiWarps + 2 + kLtConvWarps + (kTsMmaWarps - 1);     // 17
+constexpr int kTsThreads = kTsWarps * 32;                                        // 544
+
+template <bool HAS_Z, bool HAS_ACT>
+__global__ void __launch_bounds__(kTsThreads, 1)
+    umma_linear_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
+                          const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmZin,
+                          const float* __restrict__ W, int64_t M, int N, int K, int nkb, int nob, int nst, int nbuf,
+                          const float* __restrict__ bias, const float* __restrict__ prelu_slope,
+                          const float* __restrict__ act_slope, float* __restrict__ dslope_part) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stages = smem;                                               // [nst][hi slab | lo slab]
+  uint8_t* c_out = stages + (size_t)nst * kTsStage;                     // [nbuf][1 + HAS_Z][nob] slabs
+  const int out_buf_bytes = (1 + (int)HAS_Z) * nob * kTsSlab;
+  uint8_t* zin = c_out + (size_t)nbuf * out_buf_bytes;                  // [2][nob] slabs of z_in (two tiles ahead)
+  uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(zin + (size_t)(HAS_ACT ? 2 * nob : 0) * kTsSlab);
+  const uint32_t bars = smem_u32(bar_ptr);
+  const int kRawFull = 0, kLoFull = nst, kEmpty = 2 * nst, kAccFull = 3 * nst, kAccEmpty = kAccFull + 2,
+            kZinFull = kAccEmpty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + kZinFull + 2);
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  const int64_t ntiles = (M + kTsRows - 1) / kTsRows;
+  const int64_t my_tiles = (ntiles > cta) ? (ntiles - cta + ncta - 1) / ncta : 0;
+  const int64_t my_items = my_tiles * nkb;
+
+  if (tid == 0) {
+    for (int s = 0; s < nst; ++s) {
+      mbar_init(bar(kRawFull + s), 1);
+      mbar_init(bar(kLoFull + s), kLtConvThreads);
+      mbar_init(bar(kEmpty + s), kTsMmaWarps);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar(kAccFull + a), 1);
+      mbar_init(bar(kAccEmpty + a), kLtEpiThreads);
+      mbar_init(bar(kZinFull + a), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kLtMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp < kLtEpiWarps) {
+    // W -> tensor memory, rounded hi / exact lo; rows past N and columns past K are zero
+    const int c = (warp & 3) * 32 + lane;
+    const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int kbeg = (warp >> 2) * (kTsWCols / 2);
+    for (int k0 = kbeg; k0 < kbeg + kTsWCols / 2; k0 += 16) {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = k0 + 4 * q;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < N && k < K) v = __ldg(reinterpret_cast<const float4*>(W + (int64_t)c * K + k));
+        split_tf32(v.x, hi[4 * q], lo[4 * q]);
+        split_tf32(v.y, hi[4 * q + 1], lo[4 * q + 1]);
+        split_tf32(v.z, hi[4 * q + 2], lo[4 * q + 2]);
+        split_tf32(v.w, hi[4 * q + 3], lo[4 * q + 3]);
+      }
+      tmem_st16(tl + (uint32_t)k0, hi);
+      tmem_st16(tl + (uint32_t)(kTsWCols + k0), lo);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const int conv_first = kLtTmaWarp + 1, mma_extra_first = conv_first + kLtConvWarps;
+  if (warp == kLtTmaWarp) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int64_t tile = cta; tile < ntiles; tile += ncta) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(bar(kEmpty + s), ph);
+          mbar_expect_tx(bar(kRawFull + s), kTsSlab);
+          tma_load_2d(smem_u32(stages + (size_t)s * kTsStage), &tmA, kb * kKB, (int)(tile * kTsRows), bar(kRawFull + s));
+          if (++s == nst) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= conv_first && warp < mma_extra_first) {
+    // ===================== converters: lo = x - trunc_tf32(x) into the second half of the stage ============
+    const int ct = tid - conv_first * 32;          // 0..127
+    int s = 0;
+    uint32_t sph = 0;
+    for (int64_t it = 0; it < my_items; ++it) {
+      mbar_wait(bar(kRawFull + s), sph);
+      const float4* src = reinterpret_cast<const float4*>(stages + (size_t)s * kTsStage);
+      float4* dst = reinterpret_cast<float4*>(stages + (size_t)s * kTsStage + kTsSlab);
+#pragma unroll
+      for (int i = 0; i < kTsSlab / 16 / kLtConvThreads; ++i) {
+        const float4 v = src[ct + i * kLtConvThreads];
+        dst[ct + i * kLtConvThreads] = make_float4(lo_trunc(v.x), lo_trunc(v.y), lo_trunc(v.z), lo_trunc(v.w));
+      }
+      fence_proxy_async();
+      mbar_arrive(bar(kLoFull + s));
+      if (++s == nst) { s = 0; sph ^= 1; }
+    }
+  } else if (warp == kLtMmaWarp || warp >= mma_extra_first) {
+    // ===================== MMA issuers: tile t_local belongs to issuer t_local % 4 =====================
+    // Every issuer walks ALL items in ring order and waits on every barrier phase (an mbarrier parity wait is only
+    // meaningful one phase ahead), but issues -- and commits -- only for its own tiles; for the others it just
+    // signs the stage off, so a stage is released by one commit + three plain arrivals.
+    const int me = (warp == kLtMmaWarp) ? 0 : warp - mma_extra_first + 1;
+    const uint32_t idesc_wide = make_idesc(2 * kTsRows, 0, 0), idesc = make_idesc(kTsRows, 0, 0);
+    const uint32_t st_lo = desc_lo(smem_u32(stages));
+    const uint32_t w_hi = tmem_base, w_lo = tmem_base + (uint32_t)kTsWCols;
+    const bool full_k = (K & (kKB - 1)) == 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t t_local = 0; t_local < my_tiles; ++t_local) {
+      const bool mine = (int)(t_local & (kTsMmaWarps - 1)) == me;
+      const int acc = (int)(t_local & 1);
+      mbar_wait(bar(kAccEmpty + acc), (uint32_t)(((t_local >> 1) & 1) ^ 1));
+      tc_fence_after();
+      const uint32_t d_main = tmem_base + (uint32_t)(kTsAcc0 + acc * kTsAccCols), d_corr = d_main + (uint32_t)kTsRows;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(bar(kRawFull + s), ph);
+        mbar_wait(bar(kLoFull + s), ph);
+        if (mine) {
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t b = st_lo + (uint32_t)s * (kTsStage >> 4);
+            const uint32_t kc = (uint32_t)(kb * kKB);
+            if (full_k) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_tf32_ts(d_main, w_hi + kc + 8 * ks, desc_k128(b + 2 * ks), idesc_wide, (kb | ks) ? 1u : 0u);
+                umma_tf32_ts(d_corr, w_lo + kc + 8 * ks, desc_k128(b + 2 * ks), idesc, 1u);
+              }
+            } else {
+              const int ksteps = min(4, (K - kb * kKB + 7) / 8);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                umma_tf32_ts(d_main, w_hi + kc + 8 * ks, desc_k128(b + 2 * ks), idesc_wide, (kb | ks) ? 1u : 0u);
+                umma_tf32_ts(d_corr, w_lo + kc + 8 * ks, desc_k128(b + 2 * ks), idesc, 1u);
+              }
+            }
+            umma_commit(bar(kEmpty + s));
+            if (kb == nkb - 1) umma_commit(bar(kAccFull + acc));
+          }
+          __syncwarp();
+        } else if (lane == 0) {
+          mbar_arrive(bar(kEmpty + s));
+        }
+        if (++s == nst) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM (transposed tile) -> swizzled smem slabs -> TMA tensor store =====
+    const float slope = prelu_slope ? __ldg(prelu_slope) : 1.f;      // slope 1: PReLU is the identity
+    const float aslope = HAS_ACT ? __ldg(act_slope) : 0.f;
+    float dsl = 0.f;
+    const int c = (warp & 3) * 32 + lane, rh = warp >> 2;
+    const bool ch_ok = (warp & 3) < nob;                  // this warp's 32 channels have an output slab
+    const float bias_c = (bias && c < N) ? __ldg(bias + c) : 0.f;
+    // byte offset of (row r, channel c) in the [nob] swizzled slabs = c_off + r * 128 + swz[r & 7]
+    const uint32_t c_off = (uint32_t)(c >> 5) * kTsSlab + (uint32_t)(c & 3) * 4u + (uint32_t)(rh * 32 * 128);
+    uint32_t swz[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) swz[q] = c_off + (uint32_t)(((((c & 31) >> 2) ^ q) & 7) << 4);
+    const uint32_t zin_s = smem_u32(zin);
+    // z_in tiles arrive two tiles ahead, fetched by epilogue thread 0 right after the barrier that says every
+    // thread is done with the buffer
+    auto fetch_zin = [&](int64_t tile, int buf) {
+      mbar_expect_tx(bar(kZinFull + buf), (uint32_t)nob * kTsSlab);
+      for (int j = 0; j < nob; ++j)
+        tma_load_2d(zin_s + (uint32_t)(buf * nob + j) * kTsSlab, &tmZin, j * kKB, (int)(tile * kTsRows),
+                    bar(kZinFull + buf));
+    };
+    if (HAS_ACT && tid == 0) {
+      if (cta < ntiles) fetch_zin(cta, 0);
+      if (cta + ncta < ntiles) fetch_zin(cta + ncta, 1);
+    }
+    int64_t t_local = 0;
+    for (int64_t tile = cta; tile < ntiles; tile += ncta, ++t_local) {
+      const int acc = (int)(t_local & 1);
+      const uint32_t ob = smem_u32(c_out + (size_t)(nbuf == 2 ? (t_local & 1) : 0) * out_buf_bytes);
+      const uint32_t zb = ob + (uint32_t)nob * kTsSlab;
+      const uint32_t zt = zin_s + (uint32_t)(acc * nob) * kTsSlab;
+      if (nbuf == 1 && t_local > 0) {
+        if (tid == 0) bulk_wait_read();
+        named_bar(1, kLtEpiThreads);
+      }
+      mbar_wait(bar(kAccFull + acc), (uint32_t)((t_local >> 1) & 1));
+      tc_fence_after();
+      if (HAS_ACT) mbar_wait(bar(kZinFull + acc), (uint32_t)((t_local >> 1) & 1));
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kTsAcc0 + acc * kTsAccCols + rh * 32);
+      const int64_t rows_left = M - (tile * kTsRows + rh * 32);       // rows of this half that exist
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float v[16], vc[16];
+        tmem_ld16x2(taddr + 16 * i, taddr + kTsRows + 16 * i, v, vc);
+        if (ch_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t off = swz[j & 7] + (uint32_t)((16 * i + j) * 128);
+            float o = (v[j] + vc[j]) + bias_c;
+            if (HAS_ACT) {
+              const float zv = lds_f32(zt + off);
+              if (16 * i + j < rows_left) dsl += zv > 0.f ? 0.f : o * zv;
+              o = zv > 0.f ? o : aslope * o;
+            }
+            if (HAS_Z) sts_f32(zb + off, o);
+            sts_f32(ob + off, prelu_f(o, slope));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar(kAccEmpty + acc));
+      fence_proxy_async();
+      if (nbuf == 2 && tid == 0) bulk_wait_read();
+      named_bar(1, kLtEpiThreads);
+      if (tid == 0) {
+        if (HAS_ACT && tile + 2 * (int64_t)ncta < ntiles) fetch_zin(tile + 2 * (int64_t)ncta, acc);
+        for (int j = 0; j < nob; ++j) {
+          tma_store_2d(&tmC, j * kKB, (int)(tile * kTsRows), ob + (uint32_t)j * kTsSlab);
+          if (HAS_Z) tma_store_2d(&tmZ, j * kKB, (int)(tile * kTsRows), zb + (uint32_t)j * kTsSlab);
+        }
+        bulk_commit();
+      }
+    }
+    if (HAS_ACT) {                                         // per-CTA slope-gradient partial, fixed order
+      __shared__ float dsl_ts[kLtEpiWarps];
+      dsl = warp_sum(dsl);
+      if (lane == 0) dsl_ts[warp] = dsl;
+      named_bar(1, kLtEpiThreads);
+      if (tid == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLtEpiWarps; ++w) t += dsl_ts[w];
+        dslope_part[blockIdx.x] = t;
+      }
+    }
+    if (tid == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kLtMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // TMA-fed dW: the copy engine brings [32 rows x M] / [32 rows x N] boxes of dY / X (row-major, unswizzled)
 // into a raw ring; converter warps transpose + split them smem -> smem into the K-major stages.  A "unit" is
 // 32 columns x 4 rows: a lane owns one column, reads it for 4 consecutive rows (4 conflict-free LDS.32) and
@@ -1296,12 +1601,62 @@ TmaLinPlan plan_linear_tma(int64_t N, int64_t K, bool has_z, bool has_act = fals
   return p;
 }
 
+// Weights-stationary kernel for 64 < N <= 128, K <= 128 (GCL_UMMA_NO_TS=1 switches it off for A/B runs).
+static const bool g_no_ts = [] {
+  const char* e = getenv("GCL_UMMA_NO_TS");
+  return e && e[0] == '1';
+}();
+int umma_linear_ts(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
+                   const float* slope, float* z_out, const float* z_in, const float* act_slope, float* dslope_part,
+                   int* n_parts, cudaStream_t s) {
+  if (g_no_ts || N <= 64 || N > 128 || K < kKB || K > kTsWCols || (N & 3) || (K & 3)) return GCL_ERR_UNSUPPORTED;
+  const int has_z = z_out ? 1 : 0, has_act = act_slope ? 1 : 0;
+  const int nkb = (int)((K + kKB - 1) / kKB), nob = (int)((N + kKB - 1) / kKB);
+  const long fixed = 1024 + 8L * 64;
+  int nbuf = 2, nst = 0;
+  for (; nbuf >= 1; --nbuf) {      // two output buffers if at least 6 operand stages remain
+    const long out_bytes = (long)nbuf * nob * kTsSlab * (1 + has_z) + 2L * has_act * nob * kTsSlab;
+    nst = (int)(((long)kMaxSmem - out_bytes - fixed) / kTsStage);
+    if (nst >= (nbuf == 2 ? 6 : 4)) break;
+  }
+  if (nbuf < 1) return GCL_ERR_UNSUPPORTED;
+  if (nst > 10) nst = 10;
+  const size_t smem = (size_t)fixed + (size_t)nst * kTsStage + (size_t)nbuf * nob * kTsSlab * (1 + has_z) +
+                      2 * (size_t)has_act * nob * kTsSlab;
+  CUtensorMap tmA, tmC, tmZ, tmZin;
+  if (!make_map_2d(&tmA, A, M, K, kTsRows, kKB, CU_TENSOR_MAP_SWIZZLE_128B) ||
+      !make_map_2d(&tmC, C, M, N, kTsRows, kKB, CU_TENSOR_MAP_SWIZZLE_128B) ||
+      !make_map_2d(&tmZ, z_out ? z_out : C, M, N, kTsRows, kKB, CU_TENSOR_MAP_SWIZZLE_128B) ||
+      !make_map_2d(&tmZin, z_in ? z_in : C, M, N, kTsRows, kKB, CU_TENSOR_MAP_SWIZZLE_128B))
+    return GCL_ERR_UNSUPPORTED;
+  const int64_t ntiles = (M + kTsRows - 1) / kTsRows;
+  const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kTsThreads, smem, s>>>(tmA, tmC, tmZ, tmZin, W_nk, M, (int)N, (int)K, nkb, nob, nst, nbuf, bias, slope,
+                                        act_slope, dslope_part);
+    return cudaSuccess;
+  };
+  const cudaError_t e = has_act ? launch(umma_linear_ts_kernel<false, true>)
+                        : has_z ? launch(umma_linear_ts_kernel<true, false>)
+                                : launch(umma_linear_ts_kernel<false, false>);
+  if (e != cudaSuccess) return fail_cuda(e, "umma_linear_ts(smem attr)");
+  if (n_parts) *n_parts = grid;
+  GCL_CHECK_LAUNCH("umma_linear_ts");
+  return GCL_OK;
+}
+
 int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
                     const float* slope, float* z_out, const float* z_in, const float* act_slope, float* dslope_part,
                     int* n_parts, const float* att, float* sc_src, float* sc_dst, cudaStream_t s) {
   if (act_slope && (!z_in || !dslope_part || !al16(z_in) || z_out)) return GCL_ERR_UNSUPPORTED;
   if (!(al16(A) && al16(W_nk) && al16(C) && (!z_out || al16(z_out))) || M <= 0 || M > 0x7fffff00LL)
     return GCL_ERR_UNSUPPORTED;
+  if (!att) {
+    const int rc = umma_linear_ts(A, W_nk, C, M, N, K, bias, slope, z_out, z_in, act_slope, dslope_part, n_parts, s);
+    if (rc != GCL_ERR_UNSUPPORTED) return rc;
+  }
   TmaLinPlan p = plan_linear_tma(N, K, z_out != nullptr, act_slope != nullptr);
   int n_split = 1;
   if (!p.ok && N % 64 == 0) {            // too wide for one CTA's smem: two CTAs per row tile, half the columns each
