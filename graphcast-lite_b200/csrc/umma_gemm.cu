@@ -1489,6 +1489,221 @@ __global__ void __launch_bounds__(kDwThreads, 1)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// dW for wide layers (64 < M <= 128): the dY^T operand goes to TENSOR MEMORY instead of shared memory.
+// In umma_dw_tma_kernel both operands are transposed + split smem -> smem and read back by three MMAs: ~208 KB of
+// shared-memory traffic per 32-row block (32 KB of HBM data), and ncu shows the 16 converter warps, not HBM or
+// the tensor pipe, as the limit (0.62 of the HBM roofline at 128 x 128).  Here a converter thread owns output
+// channel m = TMEM lane m: it reads its column of the raw dY block for 16 consecutive rows (conflict-free
+// LDS.32), splits and writes hi / lo with two tcgen05.st -- that IS the K-major A operand.  The X side keeps the
+// K-major SWIZZLE_128B stages (hi | lo adjacent): A_hi x [B_hi | B_lo] is one MMA of N = 2 n_pad, A_lo x B_hi
+// accumulates into the correction columns.  144 KB of shared-memory traffic per block, half the converter work.
+// TMEM: columns 0 .. 2 n_pad accumulator (main | correction), 256 + 64 st .. the 4 A stages (32 hi | 32 lo).
+// 18 warps: 0-7 dY converters (warp w: lanes 32 (w % 4).., rows 16 (w / 4)..; 0-3 then run the epilogue), 8 MMA
+// issue + TMEM allocation, 9 TMA producer, 10-17 X converters.
+constexpr int kDtsStages = 4, kDtsA0 = 256, kDtsAWarps = 8, kDtsBWarps = 8;
+
+template <int NUB>
+__global__ void __launch_bounds__(kDwThreads, 1)
+    umma_dw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      float* __restrict__ part, float* __restrict__ part_colsum, int64_t R, int M, int N, int n_pad,
+                      int nraw, int raw_bytes, int64_t rows_per_cta) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_part = n_pad * 128, stage_bytes = 2 * b_part;
+  uint8_t* st_base = smem;
+  uint8_t* raw = st_base + (size_t)kDtsStages * stage_bytes;
+  uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(raw + (size_t)nraw * raw_bytes);
+  const uint32_t bars = smem_u32(bar_ptr);
+  const int kFull = 0, kEmpty = kDtsStages, kRawFull = 2 * kDtsStages, kRawEmpty = kRawFull + nraw, kAccFull = kRawEmpty + nraw;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + kAccFull + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t r_beg = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = min(R, r_beg + rows_per_cta);
+  const int64_t nkb = r_end > r_beg ? (r_end - r_beg + kKB - 1) / kKB : 0;
+  constexpr int kMmaWarp = kDtsAWarps, kTmaWarp = kDtsAWarps + 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < kDtsStages; ++s) {
+      mbar_init(bar(kFull + s), kDtsAWarps + kDtsBWarps);      // one arrival per converter warp
+      mbar_init(bar(kEmpty + s), 1);
+    }
+    for (int s = 0; s < nraw; ++s) {
+      mbar_init(bar(kRawFull + s), 1);
+      mbar_init(bar(kRawEmpty + s), kDtsAWarps + kDtsBWarps);
+    }
+    mbar_init(bar(kAccFull), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512u);
+  for (int i = tid; i < kDtsStages * stage_bytes / 16; i += kDwThreads)
+    reinterpret_cast<float4*>(st_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t raw_u32 = smem_u32(raw), st_u32 = smem_u32(st_base);
+
+  if (warp == kTmaWarp) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int64_t kb = 0; kb < nkb; ++kb) {
+        const int row = (int)(r_beg + kb * kKB);
+        mbar_wait(bar(kRawEmpty + s), ph);
+        mbar_expect_tx(bar(kRawFull + s), (uint32_t)(kKB * (M + N) * 4));
+        const uint32_t dst = raw_u32 + (uint32_t)s * (uint32_t)raw_bytes;
+        tma_load_2d(dst, &tmA, 0, row, bar(kRawFull + s));
+        tma_load_2d(dst + (uint32_t)(kKB * M * 4), &tmB, 0, row, bar(kRawFull + s));
+        if (++s == nraw) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp < kDtsAWarps) {
+    // ---- dY converters: raw [32 rows][M] -> TMEM lane m, columns = rows of the block (hi | lo)
+    const int q = warp & 3, hr = warp >> 2;
+    const int m = q * 32 + lane;
+    const bool m_ok = m < M;
+    const uint32_t pitch = (uint32_t)M * 4u;
+    const uint32_t src = (uint32_t)((16 * hr) * M + (m_ok ? m : 0)) * 4u;
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kDtsA0 + 16 * hr);
+    float cs = 0.f;
+    int st = 0, rs = 0;
+    uint32_t ph = 1, rph = 0;
+    for (int64_t kb = 0; kb < nkb; ++kb) {
+      mbar_wait(bar(kRawFull + rs), rph);
+      mbar_wait(bar(kEmpty + st), ph);
+      tc_fence_after();
+      const uint32_t a = raw_u32 + (uint32_t)rs * (uint32_t)raw_bytes + src;
+      float v[16], hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = lds_f32(a + (uint32_t)j * pitch);
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (!m_ok) v[j] = 0.f;
+        t += v[j];
+        split_tf32(v[j], hi[j], lo[j]);
+      }
+      cs += t;
+      tmem_st16(tl + (uint32_t)(st * 64), hi);
+      tmem_st16(tl + (uint32_t)(st * 64 + 32), lo);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(kFull + st));
+        mbar_arrive(bar(kRawEmpty + rs));
+      }
+      if (++st == kDtsStages) { st = 0; ph ^= 1; }
+      if (++rs == nraw) { rs = 0; rph ^= 1; }
+    }
+    if (part_colsum && m_ok) part_colsum[((int64_t)blockIdx.x * 2 + hr) * M + m] = cs;
+    if (warp < 4) {
+      // ---- epilogue: the accumulator is complete once the last MMA has retired
+      float* prow = part + ((int64_t)blockIdx.x * M + m) * N;
+      if (nkb > 0) {
+        mbar_wait(bar(kAccFull), 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < n_pad; c0 += 16) {
+          float v16[16], c16[16];
+          tmem_ld16x2(taddr + c0, taddr + n_pad + c0, v16, c16);
+          if (m_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = c0 + j;
+              if (n < N) prow[n] = v16[j] + c16[j];
+            }
+          }
+        }
+      } else if (m_ok) {
+        for (int n = 0; n < N; ++n) prow[n] = 0.f;
+      }
+    }
+  } else if (warp > kTmaWarp) {
+    // ---- X converters: (32 columns x 4 rows) units, transpose + split into the K-major stage
+    const int bw = warp - (kTmaWarp + 1);                 // 0..7
+    const int n_units = 8 * ((N + 31) / 32);
+    uint32_t src_off[NUB], dst_off[NUB];
+#pragma unroll
+    for (int i = 0; i < NUB; ++i) {
+      const int u = bw + i * kDtsBWarps;
+      const int col = (u >> 3) * 32 + lane, chunk = u & 7;
+      const bool ok = u < n_units && col < N;
+      src_off[i] = ok ? (uint32_t)(kKB * M * 4 + ((chunk * 4) * N + col) * 4) : 0xffffffffu;
+      dst_off[i] = sw_off(col, chunk);
+    }
+    const uint32_t pitch = (uint32_t)N * 4u;
+    int st = 0, rs = 0;
+    uint32_t ph = 1, rph = 0;
+    for (int64_t kb = 0; kb < nkb; ++kb) {
+      mbar_wait(bar(kRawFull + rs), rph);
+      mbar_wait(bar(kEmpty + st), ph);
+      const uint32_t rbase = raw_u32 + (uint32_t)rs * (uint32_t)raw_bytes;
+      const uint32_t sbase = st_u32 + (uint32_t)st * (uint32_t)stage_bytes;
+      float4 v[NUB];
+#pragma unroll
+      for (int i = 0; i < NUB; ++i) {
+        if (src_off[i] != 0xffffffffu) {
+          const uint32_t a = rbase + src_off[i];
+          v[i] = make_float4(lds_f32(a), lds_f32(a + pitch), lds_f32(a + 2 * pitch), lds_f32(a + 3 * pitch));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NUB; ++i) {
+        if (src_off[i] != 0xffffffffu) {
+          float4 h, l;
+          split_tf32(v[i].x, h.x, l.x);
+          split_tf32(v[i].y, h.y, l.y);
+          split_tf32(v[i].z, h.z, l.z);
+          split_tf32(v[i].w, h.w, l.w);
+          sts_f32x4(sbase + dst_off[i], h);
+          sts_f32x4(sbase + dst_off[i] + (uint32_t)b_part, l);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(kFull + st));
+        mbar_arrive(bar(kRawEmpty + rs));
+      }
+      if (++st == kDtsStages) { st = 0; ph ^= 1; }
+      if (++rs == nraw) { rs = 0; rph ^= 1; }
+    }
+  } else {
+    // ---- MMA issuer
+    const uint32_t idesc = make_idesc(n_pad, 0, 0), idesc_wide = make_idesc(2 * n_pad, 0, 0);
+    const uint32_t st_lo = desc_lo(st_u32);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int64_t kb = 0; kb < nkb; ++kb) {
+      mbar_wait(bar(kFull + st), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t b = st_lo + (uint32_t)st * ((uint32_t)stage_bytes >> 4);
+        const uint32_t a_hi = tmem_base + (uint32_t)(kDtsA0 + st * 64), a_lo = a_hi + 32u;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          umma_tf32_ts(tmem_base, a_hi + 8 * ks, desc_k128(b + 2 * ks), idesc_wide, (kb | ks) ? 1u : 0u);
+          umma_tf32_ts(tmem_base + (uint32_t)n_pad, a_lo + 8 * ks, desc_k128(b + 2 * ks), idesc, 1u);
+        }
+        umma_commit(bar(kEmpty + st));
+        if (kb == nkb - 1) umma_commit(bar(kAccFull));
+      }
+      __syncwarp();
+      if (++st == kDtsStages) { st = 0; ph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
 struct LinPlan {
   int n_pad, nkb, nst, tmem_cols, cw, stage_z;
   size_t smem;
@@ -1764,8 +1979,33 @@ int umma_dw(const float* A, const float* B, float* part, float* part_colsum, int
   if (!p.ok) return GCL_ERR_UNSUPPORTED;
   if (n_bias_parts) *n_bias_parts = p.grid;
   if (!g_force_register_staging && (M & 3) == 0 && (N & 3) == 0 && al16(A) && al16(B) && R <= 0x7fffff00LL) {
-    // raw ring + as many K-major stages as fit
     const int raw_bytes = (int)((kKB * (M + N) * 4 + 127) / 128 * 128);
+    static const bool no_dw_ts = getenv("GCL_UMMA_NO_TS") && getenv("GCL_UMMA_NO_TS")[0] == '1';
+    if (!no_dw_ts && M > 64) {          // wide layers: dY^T in tensor memory
+      const int n_pad = (int)((N + 15) / 16 * 16);
+      const size_t stage = 2 * (size_t)n_pad * 128, fixed = 1024 + 512;
+      long nraw = ((long)kMaxSmem - (long)fixed - (long)kDtsStages * (long)stage) / raw_bytes;
+      if (nraw > 10) nraw = 10;
+      CUtensorMap tmA, tmB;
+      if (nraw >= 2 && make_map_2d(&tmA, A, R, M, kKB, (int)M, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+          make_map_2d(&tmB, B, R, N, kKB, (int)N, CU_TENSOR_MAP_SWIZZLE_NONE)) {
+        const size_t smem = fixed + (size_t)kDtsStages * stage + (size_t)nraw * raw_bytes;
+        const int nub = (8 * (int)((N + 31) / 32) + kDtsBWarps - 1) / kDtsBWarps;       // 1..4
+        auto launch = [&](auto kern) -> int {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return fail_cuda(e, "umma_dw_ts(smem attr)");
+          kern<<<p.grid, kDwThreads, smem, s>>>(tmA, tmB, part, part_colsum, R, (int)M, (int)N, n_pad, (int)nraw, raw_bytes,
+                                                p.rows_per_cta);
+          return GCL_OK;
+        };
+        const int rc = nub <= 2 ? launch(umma_dw_ts_kernel<2>) : launch(umma_dw_ts_kernel<4>);
+        if (rc != GCL_OK) return rc;
+        GCL_CHECK_LAUNCH("umma_dw_ts");
+        if (n_bias_parts) *n_bias_parts = p.grid * 2;
+        return GCL_OK;
+      }
+    }
+    // raw ring + as many K-major stages as fit
     const int n_pad = (int)((N + 15) / 16 * 16);           // no ones-row here: the converters sum the columns of A
     const size_t stage = 2 * (size_t)((M + 7) / 8 * 8) * 128 + 2 * (size_t)n_pad * 128;
     const size_t fixed = 1024 + 512;
