@@ -185,6 +185,19 @@ __global__ void rows_cat_kernel(const T* __restrict__ a_c, const T* __restrict__
   }
 }
 
+// dst[b][dst_row0 + r] = src[b][src_row0 + r] for r < rows: one block of node rows of every sample, between tensors
+// with different node counts (the mesh rows of [B, G + M, C] <-> a contiguous [B, M, C])
+template <typename T>
+__global__ void rows_block_copy_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t B, int64_t e_block,
+                                       int64_t src_off, int64_t src_per, int64_t dst_off, int64_t dst_per) {
+  const int64_t total = B * e_block;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t b = i / e_block, r = i - b * e_block;
+    dst[b * dst_per + dst_off + r] = src[b * src_per + src_off + r];
+  }
+}
+
 // y[r, 0:c_out] = x[r, 0:min(c_in, c_out)], zero beyond: the slice that drops a layer's alignment padding, and its
 // backward (zero padding) -- one pass instead of torch's zero fill + strided copy
 __global__ void resize_channels_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int c_in,
@@ -294,6 +307,26 @@ extern "C" int gcl_rows_concat_f32(const float* a, const float* b_, float* out, 
   const int rc = rows_cat<true>(a, b_, out, batch, na, nb, c, stream);
   GCL_CHECK_LAUNCH("gcl_rows_concat_f32");
   return rc;
+}
+
+extern "C" int gcl_rows_block_copy_f32(const float* src, float* dst, int64_t batch, int64_t rows, int64_t c,
+                                       int64_t src_row0, int64_t src_rows, int64_t dst_row0, int64_t dst_rows,
+                                       void* stream) {
+  GCL_CHECK_ARG(src && dst && batch >= 0 && rows >= 0 && c > 0, "gcl_rows_block_copy_f32: bad argument");
+  GCL_CHECK_ARG(src_row0 >= 0 && dst_row0 >= 0 && src_row0 + rows <= src_rows && dst_row0 + rows <= dst_rows,
+                "gcl_rows_block_copy_f32: row block out of range");
+  if (batch == 0 || rows == 0) return GCL_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t eb = rows * c, so = src_row0 * c, sp = src_rows * c, d_o = dst_row0 * c, dp = dst_rows * c;
+  const bool v4 = ((eb | so | sp | d_o | dp) % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+  if (v4)
+    gcl::rows_block_copy_kernel<float4><<<gcl::blocks_for(batch * eb / 4), gcl::kT, 0, s>>>(
+        reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), batch, eb / 4, so / 4, sp / 4, d_o / 4, dp / 4);
+  else
+    gcl::rows_block_copy_kernel<float><<<gcl::blocks_for(batch * eb), gcl::kT, 0, s>>>(src, dst, batch, eb, so, sp, d_o, dp);
+  GCL_CHECK_LAUNCH("gcl_rows_block_copy_f32");
+  return GCL_OK;
 }
 
 extern "C" int gcl_rows_split_f32(const float* x, float* a, float* b_, int64_t batch, int64_t na, int64_t nb, int64_t c,

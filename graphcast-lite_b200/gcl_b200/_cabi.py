@@ -62,6 +62,7 @@ _PROTOS = {
     "gcl_assemble_input_f32": (c_int, [P, P, P, P, I64, I64, I64, I64, I64, I64, P]),
     "gcl_rows_concat_f32": (c_int, [P, P, P, I64, I64, I64, I64, P]),
     "gcl_rows_split_f32": (c_int, [P, P, P, I64, I64, I64, I64, P]),
+    "gcl_rows_block_copy_f32": (c_int, [P, P, I64, I64, I64, I64, I64, I64, I64, P]),
     "gcl_wmse_workspace_bytes": (SZ, [I64, I64, I64]),
     "gcl_wmse_f32": (c_int, [P, P, I64, P, I64, P, F32, P, P, P, I32, F32, I64, I64, I64, P, SZ, P]),
     "gcl_ar_step_f32": (c_int, [P, P, P, I64, P, P, P, I32, F32, F32, P, P, P, I32, I64, I64, I64, I64, P, SZ, P]),

@@ -12,6 +12,7 @@ Same module tree and parameter names as /root/reference/src/models.py (MLP :54-1
 The InteractionNet processor of the v2 configs (models.py:166-285) is built from the same kernels (see
 InteractionNetLayer).  Product graph and regional meshes are out of scope.
 """
+import os
 from typing import Optional
 
 import torch
@@ -382,7 +383,15 @@ class WeatherPrediction(nn.Module):
             width = (width + 3) // 4 * 4
         enc_in = _AssembleInput.apply(X, self.init_grid_features, self.init_mesh_features, width)
         enc = self.encoder(X=enc_in, edge_index=self.encoding_graph)
-        grid_lat, mesh_lat = ops.split_rows(enc, G)      # contiguous halves, one pass (and one pass back)
+        # models.py:841-842 / :865 slice the encoder output into grid and mesh rows and concatenate the grid rows with
+        # the processed mesh rows.  Here only the mesh rows move: they are copied out for the processor and its
+        # result is written back over them, so the decoder reads [grid_lat ; proc] where enc already lies.
+        in_place = os.environ.get("GCL_NO_ROW_BRIDGE") != "1"        # A/B switch: the two-copy split / concat
+        if in_place:
+            bridge = ops.RowBridge()
+            mesh_lat = ops.take_rows(enc, G, bridge)
+        else:
+            grid_lat, mesh_lat = ops.split_rows(enc, G)
         if self.using_sparse_gat:
             proc, new_ei = self.processor(X=mesh_lat, edge_index=self.processing_graph,
                                           attention_threshold=attention_threshold, **kwargs)
@@ -393,6 +402,7 @@ class WeatherPrediction(nn.Module):
         else:
             proc = self.processor(X=mesh_lat, edge_index=self.processing_graph,
                                   attention_threshold=attention_threshold)
-        dec = self.decoder(X=ops.concat_rows(grid_lat, proc), edge_index=self.decoding_graph, rows_out=G)
+        dec_in = ops.put_rows(enc, proc, G, bridge) if in_place else ops.concat_rows(grid_lat, proc)
+        dec = self.decoder(X=dec_in, edge_index=self.decoding_graph, rows_out=G)
         out = dec[:, :G]
         return out.squeeze(0) if squeeze else out

@@ -694,6 +694,94 @@ class _SplitRows(torch.autograd.Function):
         return _rows_concat_raw(da, db, B, ctx.na, n - ctx.na, C, (da if da is not None else db).device), None
 
 
+def _rows_block_copy_raw(src, dst, rows, src_row0, dst_row0):
+    B, ns, C = src.shape
+    nd = dst.shape[1]
+    with torch.cuda.device(src.device):
+        _call("gcl_rows_block_copy_f32", _p(src), _p(dst), B, rows, C, src_row0, ns, dst_row0, nd, _stream(),
+              nbytes=8 * B * rows * C, tag=f"B{B}x{rows}of{max(ns, nd)}xC{C}")
+    return dst
+
+
+class RowBridge:
+    """Shared state of one take_rows / put_rows pair (see put_rows)."""
+
+    def __init__(self):
+        self.d_full = None
+
+
+class _TakeRows(torch.autograd.Function):
+    """x [B, N, C] -> contiguous copy of x[:, n0:] (the mesh rows, models.py:842).  Backward: see put_rows."""
+
+    @staticmethod
+    def forward(ctx, x, n0, bridge):
+        xc = _chk(x, "x")
+        if xc.dim() != 3 or not 0 <= int(n0) < xc.shape[1]:
+            raise ValueError(f"gcl_b200: take_rows got {tuple(xc.shape)}, n0={n0}")
+        ctx.shape, ctx.n0, ctx.bridge = xc.shape, int(n0), bridge
+        out = torch.empty((xc.shape[0], xc.shape[1] - int(n0), xc.shape[2]), dtype=torch.float32, device=xc.device)
+        return _rows_block_copy_raw(xc, out, out.shape[1], int(n0), 0)
+
+    @staticmethod
+    def backward(ctx, d):
+        d = _chk(d, "grad_out")
+        full = ctx.bridge.d_full if ctx.bridge is not None else None
+        if full is None:               # no put_rows downstream: an ordinary gradient (zeros outside the block)
+            g = torch.zeros(ctx.shape, dtype=torch.float32, device=d.device)
+            _rows_block_copy_raw(d, g, d.shape[1], 0, ctx.n0)
+            return g, None, None
+        # put_rows' backward already handed the [B, N, C] gradient of x to autograd with this block left open:
+        # complete it in place (it is not consumed before this node has run) instead of materialising a second
+        # [B, N, C] tensor for autograd to add
+        ctx.bridge.d_full = None
+        _rows_block_copy_raw(d, full, d.shape[1], 0, ctx.n0)
+        return None, None, None
+
+
+class _PutRows(torch.autograd.Function):
+    """x[:, n0:] = rows IN PLACE, returns x: torch.cat((x[:, :n0], rows), dim=1) of models.py:865 without moving the
+    first n0 rows."""
+
+    @staticmethod
+    def forward(ctx, x, rows, n0, bridge):
+        xc, rc = _chk(x, "x"), _chk(rows, "rows")
+        if xc is not x:
+            raise ValueError("gcl_b200: put_rows needs a contiguous fp32 CUDA tensor to write into")
+        if xc.dim() != 3 or rc.dim() != 3 or rc.shape[0] != xc.shape[0] or rc.shape[2] != xc.shape[2] or \
+                rc.shape[1] + int(n0) != xc.shape[1]:
+            raise ValueError(f"gcl_b200: put_rows got {tuple(xc.shape)}, {tuple(rc.shape)}, n0={n0}")
+        ctx.n0, ctx.bridge, ctx.rows_shape = int(n0), bridge, rc.shape
+        _rows_block_copy_raw(rc, xc, rc.shape[1], 0, int(n0))
+        ctx.mark_dirty(x)
+        return x
+
+    @staticmethod
+    def backward(ctx, d):
+        d = _chk(d, "grad_out")
+        d_rows = None
+        if ctx.needs_input_grad[1]:
+            d_rows = torch.empty(ctx.rows_shape, dtype=torch.float32, device=d.device)
+            _rows_block_copy_raw(d, d_rows, d_rows.shape[1], ctx.n0, 0)
+        if not ctx.needs_input_grad[0]:
+            return None, d_rows, None, None
+        # gradient of the overwritten x: d with rows n0.. zero.  When the rows were taken from x by take_rows and
+        # went through a differentiable path, its backward fills exactly those rows of this same tensor.
+        if ctx.bridge is not None and ctx.needs_input_grad[1]:
+            ctx.bridge.d_full = d
+        else:
+            d[:, ctx.n0:].zero_()
+        return d, d_rows, None, None
+
+
+def take_rows(x, n0: int, bridge=None):
+    return _TakeRows.apply(x, n0, bridge)
+
+
+def put_rows(x, rows, n0: int, bridge=None):
+    """x[:, n0:] = rows in place (x must be a non-leaf that no other op still needs in its old state)."""
+    return _PutRows.apply(x, rows, n0, bridge)
+
+
 def concat_rows(a, b):
     return _ConcatRows.apply(a, b)
 

@@ -368,6 +368,12 @@ int gcl_rows_concat_f32(const float* a, const float* b_, float* out, int64_t bat
                         int64_t c, void* stream);
 int gcl_rows_split_f32(const float* x, float* a, float* b_, int64_t batch, int64_t na, int64_t nb, int64_t c,
                        void* stream);
+/* One block of node rows of every sample: dst[b, dst_row0 + r, :] = src[b, src_row0 + r, :], r < rows, for
+ * src [B, src_rows, C] and dst [B, dst_rows, C].  With it the host takes the mesh rows out of the encoder output
+ * (models.py:842) and writes the processed mesh rows back IN PLACE (the torch.cat of models.py:865 without
+ * moving the grid rows). */
+int gcl_rows_block_copy_f32(const float* src, float* dst, int64_t batch, int64_t rows, int64_t c,
+                            int64_t src_row0, int64_t src_rows, int64_t dst_row0, int64_t dst_rows, void* stream);
 /* Residual + latitude-weighted MSE (train.py:85-102, 203-213), forward and gradient in one pass:
  *   out = (x_last ? x_last : 0) + delta;  loss = scale * inv_wsum * sum(w (out - y)^2),  w[b,g,c] = lat_w[g]
  *   (lat_w nullable = 1; inv_wsum = 1 / sum of all weights, host-computed);

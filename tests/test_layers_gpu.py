@@ -240,6 +240,53 @@ def test_rows_concat_split_are_exact_and_inverse(B, na, nb, C):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,na,nb,C", [(2, 2048, 162, 64), (3, 100, 37, 20), (1, 7, 5, 3)])
+def test_take_put_rows_bridge_matches_slice_and_cat(B, na, nb, C):
+    """The encoder -> processor -> decoder hand-over (models.py:841-842, :865): mesh rows copied out, the processed
+    rows written back over them in place.  Values and ALL gradients equal torch's slice + cat formulation, including
+    the gradient of the tensor that was overwritten (grid rows from the consumer of the merged tensor, mesh rows
+    through the processor path)."""
+    from gcl_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + na + C)
+    x0 = torch.randn(B, na + nb, C, generator=g).to(DEV)
+    Wp = torch.randn(C, C, generator=g).to(DEV)
+    wout = torch.randn(B, na + nb, C, generator=g).to(DEV)
+
+    def run(bridge_path):
+        x = x0.clone().requires_grad_(True)
+        W = Wp.clone().requires_grad_(True)
+        enc = x * 1.5                                   # a non-leaf, like the encoder output
+        if bridge_path:
+            br = ops.RowBridge()
+            mesh = ops.take_rows(enc, na, br)
+            proc = torch.tanh(mesh @ W)
+            merged = ops.put_rows(enc, proc, na, br)
+        else:
+            mesh = enc[:, na:]
+            proc = torch.tanh(mesh @ W)
+            merged = torch.cat((enc[:, :na], proc), dim=1)
+        out = (merged * wout).sum() + (merged[:, :na] ** 2).sum()
+        out.backward()
+        return merged.detach().clone(), x.grad.clone(), W.grad.clone()
+
+    m1, gx1, gw1 = run(True)
+    m0, gx0, gw0 = run(False)
+    assert torch.equal(m1, m0)
+    torch.testing.assert_close(gx1, gx0, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(gw1, gw0, rtol=1e-5, atol=1e-5)
+    # without a differentiable path through the taken rows the overwritten block gets a zero gradient
+    x = x0.clone().requires_grad_(True)
+    enc = x * 1.5
+    merged = ops.put_rows(enc, torch.zeros(B, nb, C, device=DEV), na)
+    (merged * wout).sum().backward()
+    assert torch.equal(x.grad[:, :na], 1.5 * wout[:, :na]) and not x.grad[:, na:].any()
+    # take_rows on its own is an ordinary differentiable slice
+    x = x0.clone().requires_grad_(True)
+    (ops.take_rows(x * 1.0, na) * wout[:, na:]).sum().backward()
+    assert torch.equal(x.grad[:, na:], wout[:, na:]) and not x.grad[:, :na].any()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("R,dims", [(3000, (72, 48, 48, 64)), (2500, (64, 128, 128, 64)), (300, (30, 48, 48, 33)),
                                     (4100, (66, 96, 96, 96))])
 def test_mlp_chain_with_prelu_backward_fused_into_dx(R, dims):
