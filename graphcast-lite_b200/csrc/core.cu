@@ -26,6 +26,6 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 }  // namespace gcl
 
-extern "C" int gcl_version(void) { return 3; }
+extern "C" int gcl_version(void) { return 4; }
 extern "C" const char* gcl_last_error(void) { return gcl::g_err; }
 extern "C" long long gcl_launch_count(void) { return gcl::g_launches.load(std::memory_order_relaxed); }

@@ -403,7 +403,8 @@ namespace gcl {
 int umma_linear(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
                 const float* slope, float* z_out, cudaStream_t s, const float* z_in = nullptr,
                 const float* act_slope = nullptr, float* dslope_part = nullptr, int* n_parts = nullptr,
-                const float* att = nullptr, float* sc_src = nullptr, float* sc_dst = nullptr);
+                const float* att = nullptr, float* sc_src = nullptr, float* sc_dst = nullptr,
+                float* colsum_part = nullptr, int* n_colsum_parts = nullptr);
                                                                      // umma_gemm.cu
 int umma_dw_splits(int64_t R, int64_t M, int64_t N);
 int umma_dw(const float* A, const float* B, float* part, float* part_colsum, int64_t R, int64_t M, int64_t N,
@@ -486,16 +487,19 @@ extern "C" int gcl_prelu_bwd_f32(const float* dy, const float* x, const float* s
 
 extern "C" size_t gcl_linear_bwd_dx_prelu_workspace_bytes(int64_t rows, int64_t c_in) {
   if (rows < 0 || c_in <= 0) return 0;
-  const size_t a = gcl_prelu_bwd_workspace_bytes(rows * c_in), b = (size_t)kNumSMs * sizeof(float) + 256;
-  return a > b ? a : b;
+  // slope partials (one per CTA) + column-sum partials (two per CTA) | or the two-kernel fallback's needs
+  const size_t a = gcl_prelu_bwd_workspace_bytes(rows * c_in), c = gcl_colsum_workspace_bytes(rows, c_in);
+  const size_t b = (size_t)kNumSMs * sizeof(float) * (1 + 2 * (size_t)c_in) + 256;
+  return (a > c ? a : c) > b ? (a > c ? a : c) : b;
 }
 
 // dz_in = (dy W) * PReLU'(z_in), dslope = sum((dy W) * min(z_in, 0)): the backward of "PReLU then Linear" w.r.t. the
 // PReLU's input, in one kernel on the tcgen05 path (epilogue of the dX GEMM), else dX followed by the in-place
 // PReLU backward.
 extern "C" int gcl_linear_bwd_dx_prelu_f32(const float* dy, const float* W, const float* z_in, const float* slope,
-                                           float* dz_in, float* dslope, int64_t rows, int64_t c_in, int64_t c_out,
-                                           float* wt_scratch, void* workspace, size_t workspace_bytes, void* stream) {
+                                           float* dz_in, float* dslope, float* dcolsum, int64_t rows, int64_t c_in,
+                                           int64_t c_out, float* wt_scratch, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
   GCL_CHECK_ARG(dy && W && z_in && slope && dz_in && dslope && wt_scratch && workspace,
                 "gcl_linear_bwd_dx_prelu_f32: null pointer argument");
   GCL_CHECK_ARG(rows >= 0 && c_in > 0 && c_out > 0 && c_in <= 65536 && c_out <= 65536,
@@ -507,26 +511,35 @@ extern "C" int gcl_linear_bwd_dx_prelu_f32(const float* dy, const float* W, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (rows == 0) {
     cudaMemsetAsync(dslope, 0, sizeof(float), s);
+    if (dcolsum) cudaMemsetAsync(dcolsum, 0, sizeof(float) * c_in, s);
     return GCL_OK;
   }
   if (g_dense_mode != GCL_DENSE_FFMA && rows >= kUmmaMinRows) {
     dim3 tg((unsigned)ceil_div(c_in, 32), (unsigned)ceil_div(c_out, 32));
     transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(W, wt_scratch, (int)c_out, (int)c_in);
     GCL_CHECK_LAUNCH("gcl_linear_bwd_dx_prelu_f32(transpose)");
-    int n_parts = 0;
+    int n_parts = 0, n_cs = 0;
     float* part = static_cast<float*>(workspace);
+    float* cs_part = part + kNumSMs;
     const int rc = umma_linear(dy, wt_scratch, dz_in, rows, c_in, c_out, nullptr, nullptr, nullptr, s, z_in, slope, part,
-                               &n_parts);
+                               &n_parts, nullptr, nullptr, nullptr, dcolsum ? cs_part : nullptr, &n_cs);
     if (rc == GCL_OK) {
       reduce_partials_kernel<<<1, dim3(32, 32), 0, s>>>(part, dslope, 1, n_parts);
       GCL_CHECK_LAUNCH("gcl_linear_bwd_dx_prelu_f32(reduce)");
-      return GCL_OK;
+      if (dcolsum && n_cs > 0) {             // the wide-layer kernel summed the columns in its epilogue
+        reduce_partials_kernel<<<(unsigned)ceil_div(c_in, 32), dim3(32, 32), 0, s>>>(cs_part, dcolsum, c_in, n_cs);
+        GCL_CHECK_LAUNCH("gcl_linear_bwd_dx_prelu_f32(reduce colsum)");
+        return GCL_OK;
+      }
+      return dcolsum ? gcl_colsum_f32(dz_in, dcolsum, rows, c_in, workspace, workspace_bytes, stream) : GCL_OK;
     }
     if (rc != GCL_ERR_UNSUPPORTED) return rc;
   }
-  const int rc = gcl_linear_bwd_dx_f32(dy, W, dz_in, rows, c_in, c_out, wt_scratch, stream);
+  int rc = gcl_linear_bwd_dx_f32(dy, W, dz_in, rows, c_in, c_out, wt_scratch, stream);
   if (rc != GCL_OK) return rc;
-  return gcl_prelu_bwd_f32(dz_in, z_in, slope, dz_in, dslope, rows * c_in, workspace, workspace_bytes, stream);
+  rc = gcl_prelu_bwd_f32(dz_in, z_in, slope, dz_in, dslope, rows * c_in, workspace, workspace_bytes, stream);
+  if (rc != GCL_OK || !dcolsum) return rc;
+  return gcl_colsum_f32(dz_in, dcolsum, rows, c_in, workspace, workspace_bytes, stream);
 }
 
 extern "C" int gcl_set_dense_mode(int mode) {

@@ -1020,7 +1020,10 @@ __global__ void __launch_bounds__(kTsThreads, 1)
                           const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmZin,
                           const float* __restrict__ W, int64_t M, int N, int K, int nkb, int nob, int nst, int nbuf,
                           const float* __restrict__ bias, const float* __restrict__ prelu_slope,
-                          const float* __restrict__ act_slope, float* __restrict__ dslope_part) {
+                          const float* __restrict__ act_slope, float* __restrict__ dslope_part,
+                          float* __restrict__ colsum_part) {
+  // colsum_part (HAS_ACT only, nullable): [2 gridDim.x][N] column sums of the result over this CTA's rows, i.e.
+  // the bias gradient of the layer that produced z_in -- each epilogue thread owns a channel, so it is a register
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = smem;                                               // [nst][hi slab | lo slab]
@@ -1170,7 +1173,7 @@ __global__ void __launch_bounds__(kTsThreads, 1)
     // ===================== epilogue: TMEM (transposed tile) -> swizzled smem slabs -> TMA tensor store =====
     const float slope = prelu_slope ? __ldg(prelu_slope) : 1.f;      // slope 1: PReLU is the identity
     const float aslope = HAS_ACT ? __ldg(act_slope) : 0.f;
-    float dsl = 0.f;
+    float dsl = 0.f, csum = 0.f;
     const int c = (warp & 3) * 32 + lane, rh = warp >> 2;
     const bool ch_ok = (warp & 3) < nob;                  // this warp's 32 channels have an output slab
     const float bias_c = (bias && c < N) ? __ldg(bias + c) : 0.f;
@@ -1220,6 +1223,7 @@ __global__ void __launch_bounds__(kTsThreads, 1)
               const float zv = lds_f32(zt + off);
               if (16 * i + j < rows_left) dsl += zv > 0.f ? 0.f : o * zv;
               o = zv > 0.f ? o : aslope * o;
+              csum += o;                                  // rows past M are exact zeros (zero-filled A rows)
             }
             if (HAS_Z) sts_f32(zb + off, o);
             sts_f32(ob + off, prelu_f(o, slope));
@@ -1251,6 +1255,7 @@ __global__ void __launch_bounds__(kTsThreads, 1)
         for (int w = 0; w < kLtEpiWarps; ++w) t += dsl_ts[w];
         dslope_part[blockIdx.x] = t;
       }
+      if (colsum_part && c < N) colsum_part[((int64_t)blockIdx.x * 2 + rh) * N + c] = csum;
     }
     if (tid == 0) bulk_wait_all();
   }
@@ -1823,7 +1828,7 @@ static const bool g_no_ts = [] {
 }();
 int umma_linear_ts(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
                    const float* slope, float* z_out, const float* z_in, const float* act_slope, float* dslope_part,
-                   int* n_parts, cudaStream_t s) {
+                   int* n_parts, cudaStream_t s, float* colsum_part, int* n_colsum_parts) {
   if (g_no_ts || N <= 64 || N > 128 || K < kKB || K > kTsWCols || (N & 3) || (K & 3)) return GCL_ERR_UNSUPPORTED;
   const int has_z = z_out ? 1 : 0, has_act = act_slope ? 1 : 0;
   const int nkb = (int)((K + kKB - 1) / kKB), nob = (int)((N + kKB - 1) / kKB);
@@ -1850,7 +1855,7 @@ int umma_linear_ts(const float* A, const float* W_nk, float* C, int64_t M, int64
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kTsThreads, smem, s>>>(tmA, tmC, tmZ, tmZin, W_nk, M, (int)N, (int)K, nkb, nob, nst, nbuf, bias, slope,
-                                        act_slope, dslope_part);
+                                        act_slope, dslope_part, has_act ? colsum_part : nullptr);
     return cudaSuccess;
   };
   const cudaError_t e = has_act ? launch(umma_linear_ts_kernel<false, true>)
@@ -1858,18 +1863,22 @@ int umma_linear_ts(const float* A, const float* W_nk, float* C, int64_t M, int64
                                 : launch(umma_linear_ts_kernel<false, false>);
   if (e != cudaSuccess) return fail_cuda(e, "umma_linear_ts(smem attr)");
   if (n_parts) *n_parts = grid;
+  if (n_colsum_parts) *n_colsum_parts = (has_act && colsum_part) ? 2 * grid : 0;
   GCL_CHECK_LAUNCH("umma_linear_ts");
   return GCL_OK;
 }
 
 int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
                     const float* slope, float* z_out, const float* z_in, const float* act_slope, float* dslope_part,
-                    int* n_parts, const float* att, float* sc_src, float* sc_dst, cudaStream_t s) {
+                    int* n_parts, const float* att, float* sc_src, float* sc_dst, cudaStream_t s,
+                    float* colsum_part = nullptr, int* n_colsum_parts = nullptr) {
+  if (n_colsum_parts) *n_colsum_parts = 0;
   if (act_slope && (!z_in || !dslope_part || !al16(z_in) || z_out)) return GCL_ERR_UNSUPPORTED;
   if (!(al16(A) && al16(W_nk) && al16(C) && (!z_out || al16(z_out))) || M <= 0 || M > 0x7fffff00LL)
     return GCL_ERR_UNSUPPORTED;
   if (!att) {
-    const int rc = umma_linear_ts(A, W_nk, C, M, N, K, bias, slope, z_out, z_in, act_slope, dslope_part, n_parts, s);
+    const int rc = umma_linear_ts(A, W_nk, C, M, N, K, bias, slope, z_out, z_in, act_slope, dslope_part, n_parts, s,
+                                  colsum_part, n_colsum_parts);
     if (rc != GCL_ERR_UNSUPPORTED) return rc;
   }
   TmaLinPlan p = plan_linear_tma(N, K, z_out != nullptr, act_slope != nullptr);
@@ -1905,11 +1914,13 @@ int umma_linear_tma(const float* A, const float* W_nk, float* C, int64_t M, int6
 // the FFMA kernel), or an error.
 int umma_linear(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
                 const float* slope, float* z_out, cudaStream_t s, const float* z_in, const float* act_slope,
-                float* dslope_part, int* n_parts, const float* att, float* sc_src, float* sc_dst) {
+                float* dslope_part, int* n_parts, const float* att, float* sc_src, float* sc_dst, float* colsum_part,
+                int* n_colsum_parts) {
+  if (n_colsum_parts) *n_colsum_parts = 0;
   if (act_slope || att) {   // only the TMA kernel has the fused PReLU-backward / attention-score epilogues
     if (g_force_register_staging) return GCL_ERR_UNSUPPORTED;
     return umma_linear_tma(A, W_nk, C, M, N, K, bias, slope, z_out, z_in, act_slope, dslope_part, n_parts, att, sc_src,
-                           sc_dst, s);
+                           sc_dst, s, colsum_part, n_colsum_parts);
   }
   if (!g_force_register_staging) {
     const int rc = umma_linear_tma(A, W_nk, C, M, N, K, bias, slope, z_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,

@@ -33,7 +33,7 @@ _PROTOS = {
     "gcl_linear_fwd_scores_f32": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, P, P]),
     "gcl_linear_bwd_dx_f32": (c_int, [P, P, P, I64, I64, I64, P, P]),
     "gcl_linear_bwd_dx_prelu_workspace_bytes": (c_size_t, [I64, I64]),
-    "gcl_linear_bwd_dx_prelu_f32": (c_int, [P, P, P, P, P, P, I64, I64, I64, P, P, c_size_t, P]),
+    "gcl_linear_bwd_dx_prelu_f32": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, P, P, c_size_t, P]),
     "gcl_set_dense_mode": (c_int, [I32]),
     "gcl_get_dense_mode": (c_int, []),
     "gcl_linear_bwd_dw_workspace_bytes": (SZ, [I64, I64, I64]),
@@ -80,7 +80,7 @@ _PROTOS = {
     "gcl_adam_f32": (c_int, [P, P, P, P, I64, F32, F32, F32, F32, F32, P, P]),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class TilePlanStruct(ctypes.Structure):

@@ -246,6 +246,11 @@ class GraphLayer(nn.Module):
         mods = list(self.layers)
         n = X.size(-2)
         i = 0
+        # (z, slope): X is PReLU(z) coming out of a fused GCNConv + PReLU whose consumer is the next GCNConv's
+        # Linear -- the chain is differentiated through z and that PReLU's backward runs in the epilogue of the
+        # next layer's dX GEMM (ops.act_linear), as in MLP.forward
+        z, slope, sink = None, None, None
+        chain = os.environ.get("GCL_NO_GCN_CHAIN") != "1"
         while i < len(mods):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
@@ -259,7 +264,17 @@ class GraphLayer(nn.Module):
                     W = F.pad(W, (0, 0, 0, 4 - C % 4))
                     b = F.pad(b, (0, 4 - C % 4)) if b is not None else None
                 last = i + (2 if fuse else 1) >= len(mods)
-                h = ops.linear(X, W)
+                h = ops.act_linear(z, X, slope, W, sink=sink) if z is not None else ops.linear(X, W)
+                z, slope, sink = None, None, None
+                after = mods[i + 2] if i + 2 < len(mods) else None
+                # worth it when the next layer's dX runs on the tensor-core kernels with the fused epilogues
+                if chain and fuse and type(after) is GCNConv and C % 4 == 0 and C >= 32 and \
+                        after.out_channels >= 32 and after.out_channels % 4 == 0 and X.dtype == torch.float32:
+                    sink = ops.ColsumSink() if b is not None else None
+                    z, X = ops.aggregate_pre(h, g, NORM_GCN, b, nxt.weight, sink)
+                    slope = nxt.weight
+                    i += 2
+                    continue
                 X = ops.aggregate(h, g, NORM_GCN, b, nxt.weight if fuse else None,     # + bias + PReLU fused
                                   rows_out if last else None)
                 if C % 4:

@@ -168,21 +168,23 @@ def linear_bwd_dx_raw(dy2, W):
     return dx
 
 
-def linear_bwd_dx_prelu_raw(dy2, W, z_in2, slope):
-    """dz_in = (dy W) * PReLU'(z_in), dslope: backward of PReLU -> Linear w.r.t. the PReLU input, one kernel."""
+def linear_bwd_dx_prelu_raw(dy2, W, z_in2, slope, want_colsum=False):
+    """dz_in = (dy W) * PReLU'(z_in), dslope (and optionally the column sums of dz_in): backward of PReLU -> Linear
+    w.r.t. the PReLU input, one kernel."""
     R, cout = dy2.shape
     cin = W.shape[1]
     dz = torch.empty((R, cin), dtype=torch.float32, device=dy2.device)
     dslope = torch.empty(1, dtype=torch.float32, device=dy2.device)
+    dcs = torch.empty(cin, dtype=torch.float32, device=dy2.device) if want_colsum else None
     scratch = torch.empty(cin * cout, dtype=torch.float32, device=dy2.device)
     lib = _cabi.load()
     nb = lib.gcl_linear_bwd_dx_prelu_workspace_bytes(R, cin)
     ws = _ws(nb, dy2.device)
     with torch.cuda.device(dy2.device):
-        _call("gcl_linear_bwd_dx_prelu_f32", _p(dy2), _p(W), _p(z_in2), _p(slope), _p(dz), _p(dslope), R, cin, cout,
-              _p(scratch), _p(ws), nb, _stream(), nbytes=4 * R * (2 * cin + cout) + 4 * cin * cout,
+        _call("gcl_linear_bwd_dx_prelu_f32", _p(dy2), _p(W), _p(z_in2), _p(slope), _p(dz), _p(dslope), _p(dcs), R, cin,
+              cout, _p(scratch), _p(ws), nb, _stream(), nbytes=4 * R * (2 * cin + cout) + 4 * cin * cout,
               tag=f"R{R}x{cout}->{cin}")
-    return dz, dslope
+    return (dz, dslope, dcs) if want_colsum else (dz, dslope)
 
 
 def linear_bwd_dw_raw(dy2, x2, want_bias):
@@ -298,6 +300,52 @@ class _AggregateBF16(torch.autograd.Function):
         return dx, dbias, None, None, None
 
 
+class _AggregatePre(torch.autograd.Function):
+    """(z, a) with z = A_w x + bias and a = PReLU(z), for a consumer that differentiates through the
+    PRE-activation (ops.act_linear: the PReLU's backward then runs in the epilogue of the next layer's dX GEMM
+    instead of a separate pass over dout, z and dz).  z carries the gradient, a is a buffer."""
+
+    @staticmethod
+    def forward(ctx, x, bias, slope, graph: CSRGraph, kind: int, sink=None):
+        ctx.sink = sink
+        x3, squeeze = _as3(_chk(x, "x"))
+        if x3.shape[1] != graph.num_nodes:
+            raise ValueError(f"gcl_b200: x has {x3.shape[1]} nodes, graph has {graph.num_nodes}")
+        bias_c = _chk(bias, "bias") if bias is not None else None
+        slope_c = _chk(slope, "slope")
+        w, _ = graph.weights(kind)
+        n = graph.num_nodes
+        plan = graph.plan(False, n, n) if _tileable(x3.shape[-1]) else None
+        out, z = spmm_raw(graph.rowptr, graph.col, w, x3, n, bias_c, slope_c, True, plan, ("fwd", kind))
+        ctx.graph, ctx.kind, ctx.squeeze, ctx.has_bias = graph, kind, squeeze, bias is not None
+        if squeeze:
+            out, z = out.squeeze(0), z.squeeze(0)
+        ctx.mark_non_differentiable(out)
+        return z, out
+
+    @staticmethod
+    def backward(ctx, dz, _da=None):
+        g = ctx.graph
+        d3, _ = _as3(_chk(dz, "grad_out"))
+        dbias = dx = None
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            dbias = ctx.sink.take(d3) if ctx.sink is not None else None     # summed in the consumer's dX epilogue
+            if dbias is None:
+                dbias = colsum_raw(d3.view(-1, d3.shape[-1]))
+        if ctx.needs_input_grad[0]:
+            _, wt = g.weights(ctx.kind)
+            plan = g.plan(True, g.num_nodes, d3.shape[1]) if _tileable(d3.shape[-1]) else None
+            dx, _ = spmm_raw(g.rowptr_t, g.col_t, wt, d3, g.num_nodes, plan=plan, wkey=("bwd", ctx.kind))
+            if ctx.squeeze:
+                dx = dx.squeeze(0)
+        return dx, dbias, None, None, None, None
+
+
+def aggregate_pre(x, graph: CSRGraph, kind: int, bias, prelu_slope, sink=None):
+    """(z, a): see _AggregatePre.  Feed them to act_linear(z, a, prelu_slope, W_next[, sink=sink])."""
+    return _AggregatePre.apply(x, bias, prelu_slope, graph, kind, sink)
+
+
 def aggregate(x, graph: CSRGraph, kind: int, bias=None, prelu_slope=None, rows_out=None):
     """rows_out = n: only receivers 0..n-1 are produced ([.., n, C]); their gradient flows back to all senders.
     bf16 x: the bf16 feature-row path (no fused PReLU)."""
@@ -349,7 +397,8 @@ class _ActLinear(torch.autograd.Function):
     z_in = None: a_in is an ordinary differentiable input."""
 
     @staticmethod
-    def forward(ctx, z_in, a_in, slope_in, W, bias, slope_out):
+    def forward(ctx, z_in, a_in, slope_in, W, bias, slope_out, sink=None):
+        ctx.sink = sink
         ac, Wc = _chk(a_in, "x"), _chk(W, "weight")
         if ac.shape[-1] != Wc.shape[1]:
             raise ValueError(f"gcl_b200: linear got x[..., {ac.shape[-1]}] and weight {tuple(Wc.shape)}")
@@ -374,19 +423,39 @@ class _ActLinear(torch.autograd.Function):
         dz = dx = dsl = None
         if ctx.has_act_in:
             if ctx.needs_input_grad[0] or ctx.needs_input_grad[2]:
-                dz, dsl = linear_bwd_dx_prelu_raw(d2, W, zi, si)
+                if ctx.sink is not None:       # the producer of z_in wants colsum(dz) (its bias gradient)
+                    dz, dsl, dcs = linear_bwd_dx_prelu_raw(d2, W, zi, si, True)
+                    ctx.sink.put(dz, dcs)
+                else:
+                    dz, dsl = linear_bwd_dx_prelu_raw(d2, W, zi, si)
                 dz, dsl = dz.view(*ctx.lead, W.shape[1]), dsl.view_as(si)
         elif ctx.needs_input_grad[1]:
             dx = linear_bwd_dx_raw(d2, W).view(*ctx.lead, W.shape[1])
         dW = db = None
         if ctx.needs_input_grad[3] or (ctx.has_bias and ctx.needs_input_grad[4]):
             dW, db = linear_bwd_dw_raw(d2, x2, ctx.has_bias)
-        return dz, dx, dsl, dW, (db if ctx.has_bias else None), None
+        return dz, dx, dsl, dW, (db if ctx.has_bias else None), None, None
 
 
-def act_linear(z_in, a_in, slope_in, weight, bias=None, slope_out=None):
+class ColsumSink:
+    """Hands colsum(dz) from the backward of the consumer of a pre-activation z (act_linear) to the backward of its
+    producer (aggregate_pre), where it is the bias gradient.  Valid only for the very tensor it was computed from."""
+
+    def __init__(self):
+        self._ptr, self._cs = None, None
+
+    def put(self, dz, colsum):
+        self._ptr, self._cs = dz.data_ptr(), colsum
+
+    def take(self, dz):
+        cs = self._cs if (self._cs is not None and self._ptr == dz.data_ptr()) else None
+        self._ptr, self._cs = None, None
+        return cs
+
+
+def act_linear(z_in, a_in, slope_in, weight, bias=None, slope_out=None, sink=None):
     """See _ActLinear.  Returns y, or (z_out, a_out) when slope_out is given."""
-    return _ActLinear.apply(z_in, a_in, slope_in, weight, bias, slope_out)
+    return _ActLinear.apply(z_in, a_in, slope_in, weight, bias, slope_out, sink)
 
 
 class _LinearScores(torch.autograd.Function):

@@ -187,11 +187,14 @@ int gcl_linear_bwd_dx_f32(const float* dy, const float* W, float* dx, int64_t ro
                           int64_t c_out, float* wt_scratch, void* stream);
 /* Backward of "PReLU, then Linear" with respect to the PReLU's input z_in [rows, c_in] (the MLP of models.py:74-98
  * alternates them): dz_in = (dy W) * PReLU'(z_in), *dslope = sum((dy W) * min(z_in, 0)).  One kernel on the
- * tcgen05 path (epilogue of the dX GEMM); otherwise dX followed by an in-place PReLU backward. */
+ * tcgen05 path (epilogue of the dX GEMM); otherwise dX followed by an in-place PReLU backward.
+ * dcolsum (nullable, [c_in]): column sums of dz_in -- the bias gradient of a layer whose bias is added just before
+ * the PReLU (GCNConv: models.py:419-424); the wide-layer tcgen05 kernel accumulates them in its epilogue. */
 size_t gcl_linear_bwd_dx_prelu_workspace_bytes(int64_t rows, int64_t c_in);
 int gcl_linear_bwd_dx_prelu_f32(const float* dy, const float* W, const float* z_in, const float* slope,
-                                float* dz_in, float* dslope, int64_t rows, int64_t c_in, int64_t c_out,
-                                float* wt_scratch, void* workspace, size_t workspace_bytes, void* stream);
+                                float* dz_in, float* dslope, float* dcolsum, int64_t rows, int64_t c_in,
+                                int64_t c_out, float* wt_scratch, void* workspace, size_t workspace_bytes,
+                                void* stream);
 /* Which engine runs the dense transforms:
  *   GCL_DENSE_AUTO  tcgen05 tensor cores in 3xTF32 (hi/lo split, fp32 accumulate in TMEM; fp32-level
  *                   accuracy) when the shape fits (rows >= 2048, Cout <= 256), else FFMA   [default]

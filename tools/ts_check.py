@@ -57,11 +57,14 @@ def main():
         ref_dx = dy.double() @ W.double()
         e4 = relerr(dx, ref_dx)
         zin = torch.randn(R, cin, device=dev)
-        dz, dsl = ops.linear_bwd_dx_prelu_raw(dy, W, zin, slope)
+        dz, dsl, dcs = ops.linear_bwd_dx_prelu_raw(dy, W, zin, slope, True)
         ref_dz = torch.where(zin > 0, ref_dx, 0.25 * ref_dx)
         ref_dsl = (ref_dx * torch.where(zin > 0, torch.zeros_like(ref_dx), zin.double())).sum()
         e5 = relerr(dz, ref_dz)
         e6 = float((dsl.double() - ref_dsl).abs() / ref_dsl.abs().clamp_min(1e-30))
+        e9 = relerr(dcs, ref_dz.sum(0))
+        print(f"   dx_prelu colsum {e9:.2e}")
+        worst = max(worst, e9)
         dW, db = ops.linear_bwd_dw_raw(dy, x, True)
         e7 = relerr(dW, dy.double().t() @ x.double())
         e8 = relerr(db, dy.double().sum(0))
@@ -84,6 +87,7 @@ def main():
             ("fwd+prelu+z", lambda: ops.linear_fwd_raw(x, W, b, slope, True), 4 * R * 3 * C),
             ("dx", lambda: ops.linear_bwd_dx_raw(x, W), n1),
             ("dx_prelu", lambda: ops.linear_bwd_dx_prelu_raw(x, W, zin, slope), 4 * R * 3 * C),
+            ("dx_prelu+cs", lambda: ops.linear_bwd_dx_prelu_raw(x, W, zin, slope, True), 4 * R * 3 * C),
             ("dW+dbias", lambda: ops.linear_bwd_dw_raw(x, zin, True), n1),
         ]:
             us = timeit(fn)
