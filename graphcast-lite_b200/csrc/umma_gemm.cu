@@ -1829,7 +1829,12 @@ static const bool g_no_ts = [] {
 int umma_linear_ts(const float* A, const float* W_nk, float* C, int64_t M, int64_t N, int64_t K, const float* bias,
                    const float* slope, float* z_out, const float* z_in, const float* act_slope, float* dslope_part,
                    int* n_parts, cudaStream_t s, float* colsum_part, int* n_colsum_parts) {
-  if (g_no_ts || N <= 64 || N > 128 || K < kKB || K > kTsWCols || (N & 3) || (K & 3)) return GCL_ERR_UNSUPPORTED;
+  // <= 64 output channels use half of the 128 TMEM lanes, i.e. 4 of the 8 epilogue warps (a warp reads only its own
+  // lane quarter): measured worth it only for the variant that also stores the pre-activation (0.92 vs 0.73 at
+  // 64 -> 64); the PReLU'-epilogue variant is epilogue-bound there (0.47 vs 0.68) and stays on the row-major kernel
+  static const bool no_z64 = getenv("GCL_TS_NO_Z64") && getenv("GCL_TS_NO_Z64")[0] == '1';     // A/B switch
+  const int min_n = (z_out && !act_slope && !no_z64) ? kKB : 65;
+  if (g_no_ts || N < min_n || N > 128 || K < kKB || K > kTsWCols || (N & 3) || (K & 3)) return GCL_ERR_UNSUPPORTED;
   const int has_z = z_out ? 1 : 0, has_act = act_slope ? 1 : 0;
   const int nkb = (int)((K + kKB - 1) / kKB), nob = (int)((N + kKB - 1) / kKB);
   const long fixed = 1024 + 8L * 64;

@@ -13,8 +13,8 @@ $CMD > gpurun_out/r02_bench_nograph_$W.json 2> gpurun_out/plain.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1400 -c 340 --csv \
     --log-file gpurun_out/r02_launches_$W.csv $CMD > gpurun_out/ncu_l.log 2>&1
 # full set on the dominant kernels; the .ncu-rep is exported to CSV on the box (gpurun_out/ is capped at 64 MiB)
-ncu --set full --clock-control none -k regex:"ws_kernel|umma_dw_tma|umma_linear_tma|spmm_heavy|gat_alpha_plan" \
-    --launch-skip 400 -c 48 -o gpurun_out/r02_full_$W -f $CMD > gpurun_out/ncu_f.log 2>&1
+ncu --set full --clock-control none -k regex:"ws_kernel|umma_dw_ts|umma_dw_tma|umma_linear_ts|umma_linear_tma|spmm_heavy|gat_alpha_plan" \
+    --launch-skip 400 -c 56 -o gpurun_out/r02_full_$W -f $CMD > gpurun_out/ncu_f.log 2>&1
 ncu -i gpurun_out/r02_full_$W.ncu-rep --page raw --csv > gpurun_out/r02_full_raw_$W.csv
 rm -f gpurun_out/r02_full_$W.ncu-rep
 # then, back home:

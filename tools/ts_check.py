@@ -41,7 +41,7 @@ def main():
     print("mode:", "column-split (GCL_UMMA_NO_TS=1)" if os.environ.get("GCL_UMMA_NO_TS") == "1" else "weights-stationary")
     worst = 0.0
     for (R, cin, cout) in [(1000, 128, 128), (64, 128, 128), (12345, 96, 96), (777, 64, 128), (5000, 128, 96),
-                           (300, 32, 72), (4097, 128, 100), (50000, 20, 128), (200000, 128, 128)]:
+                           (300, 32, 72), (4097, 128, 100), (3000, 64, 64), (5000, 128, 64), (2100, 64, 32), (50000, 20, 128), (200000, 128, 128)]:
         x = torch.randn(R, cin, device=dev)
         W = torch.randn(cout, cin, device=dev) / cin ** 0.5
         b = torch.randn(cout, device=dev)
@@ -74,7 +74,7 @@ def main():
         worst = max(worst, e1, e2, e3, e4, e5)
     print("worst rel err", worst)
     assert worst < 5e-6, worst
-    for (R, C) in [(1376272, 128), (327696, 128), (2752544, 96)]:
+    for (R, C) in [(1376272, 128), (327696, 128), (2752544, 96), (1376272, 64), (786560, 64)]:
         x = torch.randn(R, C, device=dev)
         W = torch.randn(C, C, device=dev) / C ** 0.5
         b = torch.randn(C, device=dev)
