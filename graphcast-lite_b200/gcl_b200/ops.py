@@ -5,6 +5,8 @@ Every op checks its inputs and raises instead of falling back to PyTorch/CPU.  T
 """
 from typing import Optional
 
+import os
+
 import torch
 
 from . import _cabi
@@ -33,6 +35,9 @@ def _chk(t: torch.Tensor, name: str) -> torch.Tensor:
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
+
+# A/B switch: autograd's default zero-fills a full-size gradient for every unused / non-differentiable output
+_MATERIALIZE = os.environ.get("GCL_MATERIALIZE_GRADS") == "1"
 
 class KernelProfiler:
     """CUDA-event timing of every C-ABI call on the launching stream (bench.py's roofline numbers).
@@ -308,6 +313,7 @@ class _AggregatePre(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bias, slope, graph: CSRGraph, kind: int, sink=None):
         ctx.sink = sink
+        ctx.set_materialize_grads(_MATERIALIZE)     # no [B, N, C] zero fill for the gradient of the non-differentiable `a`
         x3, squeeze = _as3(_chk(x, "x"))
         if x3.shape[1] != graph.num_nodes:
             raise ValueError(f"gcl_b200: x has {x3.shape[1]} nodes, graph has {graph.num_nodes}")
@@ -325,6 +331,8 @@ class _AggregatePre(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dz, _da=None):
+        if dz is None:
+            return None, None, None, None, None, None
         g = ctx.graph
         d3, _ = _as3(_chk(dz, "grad_out"))
         dbias = dx = None
@@ -399,6 +407,7 @@ class _ActLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z_in, a_in, slope_in, W, bias, slope_out, sink=None):
         ctx.sink = sink
+        ctx.set_materialize_grads(_MATERIALIZE)     # autograd would zero-fill a full-size gradient for the buffer output
         ac, Wc = _chk(a_in, "x"), _chk(W, "weight")
         if ac.shape[-1] != Wc.shape[1]:
             raise ValueError(f"gcl_b200: linear got x[..., {ac.shape[-1]}] and weight {tuple(Wc.shape)}")
@@ -418,6 +427,8 @@ class _ActLinear(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d, _da=None):
+        if d is None:
+            return None, None, None, None, None, None, None
         x2, W, zi, si = ctx.saved_tensors
         d2 = _chk(d, "grad_out").view(-1, W.shape[0])
         dz = dx = dsl = None
@@ -465,6 +476,7 @@ class _LinearScores(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, att_src, att_dst):
+        ctx.set_materialize_grads(_MATERIALIZE)
         xc, Wc = _chk(x, "x"), _chk(W, "weight")
         if xc.shape[-1] != Wc.shape[1]:
             raise ValueError(f"gcl_b200: linear got x[..., {xc.shape[-1]}] and weight {tuple(Wc.shape)}")
@@ -490,6 +502,8 @@ class _LinearScores(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dz, _ds=None, _dd=None):
+        if dz is None:
+            return None, None, None, None
         x2, W = ctx.saved_tensors
         d2 = _chk(dz, "grad_out").view(-1, W.shape[0])
         dx = dW = None
@@ -581,6 +595,7 @@ class _GAT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, att_src, att_dst, bias, graph: CSRGraph, heads, concat, slope, want_alpha, prelu_slope=None,
                 scores=None):
+        ctx.set_materialize_grads(_MATERIALIZE)      # alpha (SparseGAT's pruning input) is a non-differentiable output
         z3, squeeze = _as3(_chk(z, "z"))
         if prelu_slope is not None and int(heads) != 1:
             raise NotImplementedError("gcl_b200: PReLU fused into GATConv needs heads == 1")
@@ -655,6 +670,8 @@ class _GAT(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dalpha=None):
+        if dout is None:
+            return (None,) * 11
         z3, asrc, adst, alpha, a_s, a_d, zpre, ps = ctx.saved_tensors
         g = ctx.graph
         B, N, HC = z3.shape
