@@ -51,13 +51,18 @@ def full(path):
             ("smsp__inst_executed.sum", "warp_inst"),
             ("sm__inst_executed_pipe_tc.sum", "tc_inst"), ("sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active", "tc_pct")]
     cols = [(m, n) for m, n in cols if m in hdr]
+    units = rows[1]
+    to_mb = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}       # ncu picks the byte unit per report
     print("kernel," + ",".join(n for _, n in cols))
     for r in data:
         vals = []
-        for m, _ in cols:
+        for m, n in cols:
             v = r[hdr.index(m)].replace(",", "")
             try:
-                vals.append(f"{float(v):.4g}")
+                f = float(v)
+                if n.endswith("_MB"):
+                    f *= to_mb.get(units[hdr.index(m)], 1.0)
+                vals.append(f"{f:.4g}")
             except ValueError:
                 vals.append(v)
         print('"' + short(r[hdr.index("Kernel Name")]) + '",' + ",".join(vals))
