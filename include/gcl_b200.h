@@ -169,8 +169,10 @@ int gcl_spmm_tiled_bf16(const gcl_tile_plan* plan, const int32_t* ent, const int
  * K7  node-wise dense transform  y = act(x W^T + b)  (torch.nn.Linear in MLP, models.py:74-98, and the
  *   bias-free `lin` inside GCNConv/GATConv).  x [R, Cin], W [Cout, Cin], y [R, Cout].  Default engine:
  *   tcgen05 tensor cores in 3xTF32 (hi/lo operand split, fp32 accumulation in TMEM, TMA in and out) -- fp32-level
- *   accuracy (rms error vs fp64 2.9e-7); rows < 2048 or widths that are not a multiple of 4 floats, and
- *   gcl_set_dense_mode(GCL_DENSE_FFMA), take the fp32 FFMA kernels.
+ *   accuracy (rms error vs fp64 2.9e-7).  Layers with 64 < Cout <= 128 and Cin <= 128 run weights-stationary: W is
+ *   the M-side operand held in tensor memory and the transposed tile W x^T is accumulated (dW likewise keeps dY^T
+ *   in tensor memory); narrower layers keep W in shared memory.  rows < 2048 or widths that are not a multiple of
+ *   4 floats, and gcl_set_dense_mode(GCL_DENSE_FFMA), take the fp32 FFMA kernels.
  *   bias / prelu_slope / z_out nullable (z_out = value before PReLU).
  *   wt_scratch: device scratch of Cin*Cout floats (holds the split / transposed W).
  */
