@@ -677,8 +677,11 @@ class _GAT(torch.autograd.Function):
         B, N, HC = z3.shape
         H, C = ctx.H, ctx.C
         d3, _ = _as3(_chk(dout, "grad_out"))
-        dslope = None
-        if ctx.has_prelu:
+        dslope = dbias = None
+        if ctx.has_prelu and ctx.has_bias:
+            d3, dslope, dbias = prelu_bwd_colsum_raw(d3, zpre, ps)        # PReLU backward + bias gradient, one pass
+            dslope = dslope.view_as(ps)
+        elif ctx.has_prelu:
             d3, dslope = prelu_bwd_raw(d3, zpre, ps)
             dslope = dslope.view_as(ps)
         dev = z3.device
@@ -713,7 +716,8 @@ class _GAT(torch.autograd.Function):
                       tag=f"N{N}xH{H}xC{C}xB{B}")
             _call("gcl_gat_datt_f32", _p(z3), _p(da_s), _p(da_d), _p(datt_s), _p(datt_d), B * N, H, C, _p(ws), nb,
                   _stream(), nbytes=4 * B * N * (H * C + 2 * H), tag=f"R{B * N}xH{H}xC{C}")
-        dbias = colsum_raw(d3.view(-1, d3.shape[-1])) if ctx.has_bias else None
+        if ctx.has_bias and dbias is None:
+            dbias = colsum_raw(d3.view(-1, d3.shape[-1]))
         if ctx.squeeze:
             dz = dz.squeeze(0)
         return dz, datt_s.view(1, H, C), datt_d.view(1, H, C), dbias, None, None, None, None, None, dslope, None
