@@ -211,13 +211,27 @@ __global__ void rows_block_copy_kernel(const T* __restrict__ src, T* __restrict_
 // y[r, 0:c_out] = x[r, 0:min(c_in, c_out)], zero beyond: the slice that drops a layer's alignment padding, and its
 // backward (zero padding) -- one pass instead of torch's zero fill + strided copy
 __global__ void resize_channels_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int c_in,
-                                       int c_out) {
-  const int64_t total = rows * c_out;
+                                       int c_out, int vec) {
+  // four consecutive output floats per thread (one 64-bit division, one 16-byte store when y is 16-byte aligned)
+  const int64_t total = rows * c_out, groups = (total + 3) / 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t r = i / c_out;
-    const int c = (int)(i - r * c_out);
-    y[i] = c < c_in ? x[r * c_in + c] : 0.f;
+  for (int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gi < groups; gi += stride) {
+    const int64_t i = gi * 4;
+    int64_t r = i / c_out;
+    int c = (int)(i - r * c_out);
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = (i + k < total && c < c_in) ? __ldg(x + r * c_in + c) : 0.f;
+      if (++c == c_out) { c = 0; ++r; }
+    }
+    if (vec && i + 3 < total) {
+      *reinterpret_cast<float4*>(y + i) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i + k < total) y[i + k] = v[k];
+    }
   }
 }
 
@@ -392,8 +406,8 @@ extern "C" int gcl_ar_step_bwd_f32(const float* g_loss, const float* dloss, cons
 extern "C" int gcl_resize_channels_f32(const float* x, float* y, int64_t rows, int64_t c_in, int64_t c_out, void* stream) {
   GCL_CHECK_ARG(x && y && rows >= 0 && c_in > 0 && c_out > 0, "gcl_resize_channels_f32: bad argument");
   if (rows == 0) return GCL_OK;
-  resize_channels_kernel<<<blocks_for(rows * c_out), kT, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rows, (int)c_in,
-                                                                                               (int)c_out);
+  resize_channels_kernel<<<blocks_for((rows * c_out + 3) / 4), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, y, rows, (int)c_in, (int)c_out, (reinterpret_cast<uintptr_t>(y) & 15u) == 0 ? 1 : 0);
   GCL_CHECK_LAUNCH("gcl_resize_channels_f32");
   return GCL_OK;
 }

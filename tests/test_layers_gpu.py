@@ -240,6 +240,25 @@ def test_rows_concat_split_are_exact_and_inverse(B, na, nb, C):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("rows,cin,cout", [(1000, 20, 19), (1000, 19, 20), (7, 33, 36), (5, 4, 3), (1, 1, 4),
+                                           (4099, 16, 15), (3, 15, 16)])
+def test_resize_channels_matches_slice_and_pad(rows, cin, cout):
+    """x[..., :c] / zero padding to c channels (the alignment padding of layers with odd widths), forward and backward,
+    bit-exact against torch's slice / F.pad."""
+    import torch.nn.functional as F
+    from gcl_b200 import ops
+    g = torch.Generator().manual_seed(rows + 31 * cin + cout)
+    x = torch.randn(2, rows, cin, generator=g).to(DEV).requires_grad_(True)
+    w = torch.randn(2, rows, cout, generator=g).to(DEV)
+    y = ops.resize_channels(x, cout)
+    ref = x.detach()[..., :cout] if cout <= cin else F.pad(x.detach(), (0, cout - cin))
+    assert y.is_contiguous() and torch.equal(y, ref)
+    (y * w).sum().backward()
+    gref = F.pad(w, (0, cin - cout)) if cout <= cin else w[..., :cin]
+    assert torch.equal(x.grad, gref)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("B,na,nb,C", [(2, 2048, 162, 64), (3, 100, 37, 20), (1, 7, 5, 3)])
 def test_take_put_rows_bridge_matches_slice_and_cat(B, na, nb, C):
     """The encoder -> processor -> decoder hand-over (models.py:841-842, :865): mesh rows copied out, the processed
