@@ -15,7 +15,7 @@ DEV = "cuda:0"
 # fewer rows than one tile, the 32..64-channel variant that stores the pre-activation, narrow K (FFMA / row-major path)
 SHAPES = [(2048, 128, 128), (2111, 128, 128), (12345, 96, 96), (2777, 64, 128), (5000, 128, 96), (2300, 32, 72),
           (4097, 128, 100), (3000, 64, 64), (5000, 128, 64), (2100, 64, 32), (2500, 44, 128), (50000, 20, 128),
-          (200000, 128, 128)]
+          (200000, 128, 128), (2049, 36, 68), (2100, 100, 124), (2048, 128, 68), (3333, 40, 128), (9473, 128, 72)]
 
 
 def _relerr(a, ref):
