@@ -1798,7 +1798,10 @@ TmaLinPlan plan_linear_tma(int64_t N, int64_t K, bool has_z, bool has_act = fals
   p.n_pad = (int)((N + 15) / 16 * 16);
   p.nkb = (int)((K + kKB - 1) / kKB);
   p.nob = (int)((N + kKB - 1) / kKB);
-  if (N < kKB || K < kKB || p.n_pad > 256 || (N & 3) || (K & 3)) return p;
+  // narrow layers (the 19/20-channel output head): boxes are wider than the tensor, the tensor map zero-fills loads
+  // and clips stores
+  static const int min_w = getenv("GCL_TMA_MIN_WIDTH") ? atoi(getenv("GCL_TMA_MIN_WIDTH")) : 8;
+  if (N < min_w || K < min_w || p.n_pad > 256 || (N & 3) || (K & 3)) return p;
   const long w_bytes = 2L * p.nkb * p.n_pad * 128;
   const long fixed = 1024 + 512 + 4L * p.n_pad * 3 + 4L * 2 * 2 * kTileM * 2;   // bias, att, score partials
   long slabs = 0, out_bytes = 0;

@@ -41,7 +41,7 @@ def main():
     print("mode:", "column-split (GCL_UMMA_NO_TS=1)" if os.environ.get("GCL_UMMA_NO_TS") == "1" else "weights-stationary")
     worst = 0.0
     for (R, cin, cout) in [(1000, 128, 128), (64, 128, 128), (12345, 96, 96), (777, 64, 128), (5000, 128, 96),
-                           (300, 32, 72), (4097, 128, 100), (3000, 64, 64), (5000, 128, 64), (2100, 64, 32), (50000, 20, 128), (200000, 128, 128)]:
+                           (300, 32, 72), (4097, 128, 100), (3000, 64, 64), (5000, 128, 64), (2100, 64, 32), (4000, 64, 20), (4000, 20, 64), (3000, 12, 8), (50000, 20, 128), (200000, 128, 128)]:
         x = torch.randn(R, cin, device=dev)
         W = torch.randn(cout, cin, device=dev) / cin ** 0.5
         b = torch.randn(cout, device=dev)
@@ -74,6 +74,17 @@ def main():
         worst = max(worst, e1, e2, e3, e4, e5)
     print("worst rel err", worst)
     assert worst < 5e-6, worst
+    for (R, cin, cout) in [(1376272, 64, 20), (1376272, 20, 64)]:
+        x = torch.randn(R, cin, device=dev)
+        W = torch.randn(cout, cin, device=dev) / cin ** 0.5
+        b = torch.randn(cout, device=dev)
+        dy = torch.randn(R, cout, device=dev)
+        slope = torch.tensor([0.25], device=dev)
+        nb = 4 * R * (cin + cout)
+        for name, fn in [("fwd", lambda: ops.linear_fwd_raw(x, W, b, None, False)), ("dx", lambda: ops.linear_bwd_dx_raw(dy, W)),
+                         ("dW+dbias", lambda: ops.linear_bwd_dw_raw(dy, x, True))]:
+            us = timeit(fn)
+            print(f"R{R} {cin}->{cout} {name:10s} {us:8.1f} us  {nb / us / 1e3:7.0f} GB/s  {nb / us / 1e3 / PEAK:5.2f}", flush=True)
     for (R, C) in [(1376272, 128), (327696, 128), (2752544, 96), (1376272, 64), (786560, 64)]:
         x = torch.randn(R, C, device=dev)
         W = torch.randn(C, C, device=dev) / C ** 0.5
