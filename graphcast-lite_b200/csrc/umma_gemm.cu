@@ -1438,10 +1438,16 @@ __global__ void __launch_bounds__(kDwThreads, 1)
             for (int j = 0; j < 16; ++j) v16[j] += c1[j] + c2[j];
           }
           if (m < M) {
+            if (c0 + 16 <= N && (N & 3) == 0 && al16_dev(part)) {          // 16-byte stores
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int n = c0 + j;
-              if (n < N) prow[n] = v16[j];
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(v16[j], v16[j + 1], v16[j + 2], v16[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int n = c0 + j;
+                if (n < N) prow[n] = v16[j];
+              }
             }
           }
         }
@@ -1616,10 +1622,17 @@ __global__ void __launch_bounds__(kDwThreads, 1)
           float v16[16], c16[16];
           tmem_ld16x2(taddr + c0, taddr + n_pad + c0, v16, c16);
           if (m_ok) {
+            if (c0 + 16 <= N && (N & 3) == 0 && al16_dev(part)) {          // 16-byte stores
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int n = c0 + j;
-              if (n < N) prow[n] = v16[j] + c16[j];
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(v16[j] + c16[j], v16[j + 1] + c16[j + 1],
+                                                                        v16[j + 2] + c16[j + 2], v16[j + 3] + c16[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int n = c0 + j;
+                if (n < N) prow[n] = v16[j] + c16[j];
+              }
             }
           }
         }
