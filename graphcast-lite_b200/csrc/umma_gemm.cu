@@ -1215,12 +1215,17 @@ __global__ void __launch_bounds__(kTsThreads, 1)
         float v[16], vc[16];
         tmem_ld16x2(taddr + 16 * i, taddr + kTsRows + 16 * i, v, vc);
         if (ch_ok) {
+          float zq[16];
+          if (HAS_ACT) {          // all 16 loads first: the asm loads / stores below keep their program order, and a
+#pragma unroll                    // load behind every store would put a shared-memory round trip on every element
+            for (int j = 0; j < 16; ++j) zq[j] = lds_f32(zt + swz[j & 7] + (uint32_t)((16 * i + j) * 128));
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const uint32_t off = swz[j & 7] + (uint32_t)((16 * i + j) * 128);
             float o = (v[j] + vc[j]) + bias_c;
             if (HAS_ACT) {
-              const float zv = lds_f32(zt + off);
+              const float zv = zq[j];
               if (16 * i + j < rows_left) dsl += zv > 0.f ? 0.f : o * zv;
               o = zv > 0.f ? o : aslope * o;
               csum += o;                                  // rows past M are exact zeros (zero-filled A rows)
@@ -1849,7 +1854,9 @@ int umma_linear_ts(const float* A, const float* W_nk, float* C, int64_t M, int64
   // lane quarter): measured worth it only for the variant that also stores the pre-activation (0.92 vs 0.73 at
   // 64 -> 64); the PReLU'-epilogue variant is epilogue-bound there (0.47 vs 0.68) and stays on the row-major kernel
   static const bool no_z64 = getenv("GCL_TS_NO_Z64") && getenv("GCL_TS_NO_Z64")[0] == '1';     // A/B switch
-  const int min_n = (z_out && !act_slope && !no_z64) ? kKB : 65;
+  // (... and the PReLU'-epilogue variant when the caller also wants the column sums, which only this kernel gets for
+  // free: 256 vs 318 us at R = 1 376 272, 64 -> 64; without them the row-major kernel is level, 237 vs 248 us)
+  const int min_n = ((z_out && !act_slope && !no_z64) || (act_slope && colsum_part && !no_z64)) ? kKB : 65;
   if (g_no_ts || N < min_n || N > 128 || K < kKB || K > kTsWCols || (N & 3) || (K & 3)) return GCL_ERR_UNSUPPORTED;
   const int has_z = z_out ? 1 : 0, has_act = act_slope ? 1 : 0;
   const int nkb = (int)((K + kKB - 1) / kKB), nob = (int)((N + kKB - 1) / kKB);

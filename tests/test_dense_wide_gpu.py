@@ -51,7 +51,9 @@ def test_wide_linear_kernels_against_fp64(R, cin, cout):
     assert abs(float(dsl) - float(ref_dsl)) <= 1e-5 * float((ref_dx * zd.clamp(max=0)).abs().sum())
     assert _relerr(dcs, ref_dz.sum(0)) < 5e-6
     dz2, dsl2 = ops.linear_bwd_dx_prelu_raw(dy, W, zin, slope)
-    assert torch.equal(dz2, dz) and torch.equal(dsl2, dsl)
+    # (for <= 64 channels the variant with column sums runs on the weights-stationary kernel, the one without on the
+    # row-major kernel: same three products, different accumulation order)
+    assert _relerr(dz2, dz.double()) < 1e-6 and abs(float(dsl2) - float(dsl)) <= 1e-5 * float((ref_dx * zd.clamp(max=0)).abs().sum())
     dW, db = ops.linear_bwd_dw_raw(dy, x, True)
     assert _relerr(dW, dyd.t() @ xd) < 5e-6 and _relerr(db, dyd.sum(0)) < 5e-6
     # deterministic: same bits on a second call
